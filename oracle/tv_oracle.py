@@ -81,10 +81,11 @@ def _sl(axis, s, ndim=4):
     return tuple(idx)
 
 
-def _effective_kind(kind, L):
-    """Centred differences on an axis of length 2 fall back to the forward difference
-    (tv_operators_CPU.py:339-340 for z, :347-348 for time)."""
-    return "f" if (kind == "c" and L == 2) else kind
+def _effective_kind(kind, L, axis):
+    """Centred differences on a z or time axis of length 2 fall back to the forward difference
+    (tv_operators_CPU.py:339-340 for z, :347-348 for time).  Rows and columns have no such fallback:
+    a 2x2 image simply has zero centred differences (:331-334)."""
+    return "f" if (kind == "c" and L == 2 and axis in (_AX_Z, _AX_T)) else kind
 
 
 # ----------------------------------------------------------------------------- axis primitives
@@ -93,7 +94,7 @@ def _difference(x, axis, kind):
     tv_operators_CPU.py:115, :196, :262, :328)."""
     L = x.shape[axis]
     out = np.zeros_like(x)
-    kind = _effective_kind(kind, L)
+    kind = _effective_kind(kind, L, axis)
     if L < 2:
         return out
     if kind == "f":      # :265-268
@@ -110,7 +111,7 @@ def _adjoint_accumulate(out, p, axis, kind, weight=None):
     """Exact transpose of `_difference`: entries of p where the difference is structurally zero are
     ignored (tv_operators_CPU.py:555-560 forward, :488-493 backward, :623-628 centred)."""
     L = p.shape[axis]
-    kind = _effective_kind(kind, L)
+    kind = _effective_kind(kind, L, axis)
     if L < 2:
         return
     if kind == "f":

@@ -1,0 +1,249 @@
+"""Fused Chambolle-Pock TV denoising: two HBM passes per iteration, state resident on the device.
+
+The reference ships no solver, only the loop in README.md:139-158 (and examples/a_getting_started.ipynb
+cell 5) that users build from D_hybrid / D_T_hybrid / compute_L21_norm with all point-wise maths on the
+host.  This module is that loop as a library:
+
+  variant="readme"  the README's "simple" iteration, state (x, y_f, y_tv): bit-for-bit the same update order
+  variant="rof"     Chambolle & Pock (2011) Alg. 1 for 0.5|x-x0|^2 + lam TV(x), state (x, xbar, y): exact
+                    prox of the data term and over-relaxation
+
+Each iteration is pass A (dual: D(xbar), projection onto the lam-ball, L21 partial sums) and pass B (primal:
+D^T y, data-term update, over-relaxation, fidelity partial sums), i.e. `pytvb_cp_dual` + `pytvb_cp_primal_*`.
+
+Multi-GPU: one process per GPU, each owning a contiguous slab of z planes (the layout is z-major, so a slab
+is one contiguous byte range; README.md:235).  Before pass A the boundary planes of xbar go to the two
+z-neighbours, before pass B the boundary planes of the z-components of y; the energy needs one all-reduce
+of two doubles.  M and N are never split.  With the z axis off the slabs are independent.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _dev, _lib
+
+
+def partition_z(Nz_global, world_size):
+    """Contiguous, balanced z-slabs: [(offset, count)] for every rank (earlier ranks take the remainder)."""
+    if Nz_global < world_size:
+        raise ValueError("cannot split %d planes over %d ranks" % (Nz_global, world_size))
+    base, rem = divmod(Nz_global, world_size)
+    out, off = [], 0
+    for r in range(world_size):
+        n = base + (1 if r < rem else 0)
+        out.append((off, n))
+        off += n
+    return out
+
+
+def operator_norm_sq_bound(scheme, z_on, t_on, reg_z_over_reg, reg_time, factor_reg_static, has_mask_static):
+    """Upper bound of |D|^2: 4 per unit-weight axis for the one-sided schemes and hybrid, 1 for central."""
+    w = 2.0
+    if z_on:
+        w += reg_z_over_reg
+    if t_on:
+        w += reg_time * (max(1.0, factor_reg_static) if has_mask_static else 1.0)
+    return w if scheme == "central" else 4.0 * w
+
+
+class CudaOps:
+    """The product path: every pass is one call into libpytv_b200.so on the current stream."""
+
+    def __init__(self):
+        self.lib = _lib.lib()
+
+    def cp_dual(self, pb, xbar, y, lam, sigma, d_l21, lo, hi, ws):
+        _lib.check(self.lib.pytvb_cp_dual(ctypes.byref(pb), _dev.ptr(xbar), _dev.ptr(y), lam, sigma, _dev.ptr(d_l21), _dev.ptr(lo), _dev.ptr(hi),
+                                          _dev.ptr(ws), _dev.stream_ptr()))
+
+    def cp_primal(self, variant, pb, y, x, aux, x0, tau, c2, d_fid, lo, hi, ws):
+        fn = self.lib.pytvb_cp_primal_rof if variant == "rof" else self.lib.pytvb_cp_primal_readme
+        _lib.check(fn(ctypes.byref(pb), _dev.ptr(y), _dev.ptr(x), _dev.ptr(aux), _dev.ptr(x0), tau, c2, _dev.ptr(d_fid), _dev.ptr(lo), _dev.ptr(hi),
+                      _dev.ptr(ws), _dev.stream_ptr()))
+
+    def workspace(self, pb, device):
+        return _dev.reduce_workspace(pb, device)
+
+
+class HaloExchange:
+    """Nearest-neighbour plane exchange between z-slabs over torch.distributed (NCCL send/recv on NVLink;
+    gloo in the CPU tests)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.prev = self.rank - 1 if self.rank > 0 else None
+        self.next = self.rank + 1 if self.rank < self.world - 1 else None
+
+    def _global(self, r):
+        return r if self.group is None else self.dist.get_global_rank(self.group, r)
+
+    def exchange(self, to_prev, to_next, from_prev, from_next):
+        """Send plane `to_prev` to rank-1 and `to_next` to rank+1; receive into `from_prev` / `from_next`.
+        Any of the four may be None (direction not needed by the scheme)."""
+        ops = []
+        P2P = self.dist.P2POp
+        if self.prev is not None:
+            if to_prev is not None:
+                ops.append(P2P(self.dist.isend, to_prev, self._global(self.prev), self.group))
+            if from_prev is not None:
+                ops.append(P2P(self.dist.irecv, from_prev, self._global(self.prev), self.group))
+        if self.next is not None:
+            if to_next is not None:
+                ops.append(P2P(self.dist.isend, to_next, self._global(self.next), self.group))
+            if from_next is not None:
+                ops.append(P2P(self.dist.irecv, from_next, self._global(self.next), self.group))
+        if ops:
+            for req in self.dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def allreduce_sum(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return t
+
+
+class CPSolver:
+    """Device-resident Chambolle-Pock state for one volume, or for this rank's z-slab of a sharded volume.
+
+    x0 : (Nz_local, M, Ni, Nj) numpy array or tensor - the noisy data of this rank's slab.
+    distributed : True to shard over torch.distributed's default group (or pass `group`); the slab position is
+                  derived from the rank with `partition_z` unless z_offset / Nz_global are given.
+    """
+
+    def __init__(self, x0, lam, scheme="hybrid", variant="rof", sigma=0.5, tau=None, theta=1.0, sigma_A=1.0, reg_z_over_reg=1.0,
+                 reg_time=0.0, mask_static=False, factor_reg_static=0, distributed=False, group=None, z_offset=None, Nz_global=None,
+                 ops=None, track_energy=True):
+        if scheme not in _dev.SCHEMES:
+            raise ValueError("unknown scheme %r" % (scheme,))
+        if variant not in ("rof", "readme"):
+            raise ValueError("variant must be 'rof' or 'readme'")
+        self.ops = ops if ops is not None else CudaOps()
+        self.scheme, self.variant = scheme, variant
+        self.lam, self.sigma, self.theta, self.sigma_A = float(lam), float(sigma), float(theta), float(sigma_A)
+        self.track_energy = track_energy
+        shape = _dev.image_shape(x0)
+        if ops is None:
+            self.x0, _ = _dev.to_device(x0)
+            if self.x0.data_ptr() == (x0.data_ptr() if isinstance(x0, torch.Tensor) else 0):
+                self.x0 = self.x0.clone()
+        else:   # injected executor (CPU tests): keep the array where it is
+            self.x0 = torch.as_tensor(np.ascontiguousarray(x0)).clone() if not isinstance(x0, torch.Tensor) else x0.clone().contiguous()
+        dev, dt = self.x0.device, self.x0.dtype
+        self.halo = HaloExchange(group) if (distributed or group is not None) else None
+        if self.halo is not None and self.halo.world > 1:
+            if Nz_global is None:
+                counts = torch.zeros(self.halo.world, dtype=torch.int64, device=dev)
+                counts[self.halo.rank] = shape[0]
+                self.halo.allreduce_sum(counts)
+                Nz_global = int(counts.sum().item())
+                z_offset = int(counts[: self.halo.rank].sum().item())
+        else:
+            self.halo = None
+        self.z_offset = int(z_offset or 0)
+        self.Nz_global = int(Nz_global if Nz_global is not None else shape[0])
+        self.shape = shape
+        self._ms = None
+        if not isinstance(mask_static, bool):
+            if ops is None:
+                self._ms = _dev.mask_static_to_device(mask_static, shape[2], shape[3])
+            else:
+                m = mask_static if isinstance(mask_static, torch.Tensor) else torch.as_tensor(np.asarray(mask_static))
+                self._ms = (m.reshape(shape[2], shape[3]) != 0).to(torch.uint8).contiguous()
+        self.pb = _lib.make_problem(scheme, _lib.F32 if dt == torch.float32 else _lib.F64, shape, float(reg_z_over_reg), float(reg_time),
+                                    float(factor_reg_static), self._ms.data_ptr() if self._ms is not None else None, self.z_offset,
+                                    self.Nz_global)
+        self.z_on = self.Nz_global > 1 and float(reg_z_over_reg) > 0
+        self.t_on = shape[1] > 1 and float(reg_time) > 0
+        self.Nd = (4 + 2 * self.z_on + 2 * self.t_on) if scheme == "hybrid" else (2 + self.z_on + self.t_on)
+        if tau is None:
+            L2 = operator_norm_sq_bound(scheme, self.z_on, self.t_on, float(reg_z_over_reg), float(reg_time), float(factor_reg_static),
+                                        self._ms is not None)
+            tau = 1.0 / (L2 + 1.0)
+        self.tau = float(tau)
+        # state
+        self.x = self.x0.clone()
+        self.aux = self.x0.clone() if variant == "rof" else torch.zeros_like(self.x0)   # xbar | y_f
+        self.y = torch.zeros((shape[0], self.Nd) + shape[1:], dtype=dt, device=dev)
+        self.scal = torch.zeros(2, dtype=torch.float64, device=dev)   # [L21(D xbar), |x - x0|^2] of this slab
+        self.ws = self.ops.workspace(self.pb, dev)
+        self.iterations = 0
+        # halo planes
+        self._img_lo = self._img_hi = self._fld_lo = self._fld_hi = None
+        if self.halo is not None and self.z_on:
+            plane = (shape[1], shape[2], shape[3])
+            interior_lo, interior_hi = self.halo.prev is not None, self.halo.next is not None
+            need_img_lo, need_img_hi = scheme != "upwind", scheme != "downwind"
+            need_fld_lo, need_fld_hi = scheme != "downwind", scheme != "upwind"
+            mk = lambda: torch.empty(plane, dtype=dt, device=dev)
+            self._img_lo = mk() if (interior_lo and need_img_lo) else None
+            self._img_hi = mk() if (interior_hi and need_img_hi) else None
+            self._fld_lo = mk() if (interior_lo and need_fld_lo) else None
+            self._fld_hi = mk() if (interior_hi and need_fld_hi) else None
+        self._zf = 4 if scheme == "hybrid" else 2   # forward-type z slot of y
+        self._zb = 5 if scheme == "hybrid" else 2   # backward-type z slot
+
+    # -- the image the dual pass differentiates: xbar (rof) or x (readme, README.md:149)
+    def _dual_input(self):
+        return self.aux if self.variant == "rof" else self.x
+
+    def _exchange_image_halos(self):
+        if self.halo is None or not self.z_on:
+            return
+        src = self._dual_input()
+        scheme = self.scheme
+        # my first plane is the neighbour's halo_hi (needed unless downwind); my last plane its halo_lo (unless upwind)
+        to_prev = src[0] if scheme != "downwind" else None
+        to_next = src[-1] if scheme != "upwind" else None
+        self.halo.exchange(to_prev, to_next, self._img_lo, self._img_hi)
+
+    def _exchange_field_halos(self):
+        if self.halo is None or not self.z_on:
+            return
+        scheme = self.scheme
+        # the neighbour's adjoint reads my backward-type z slot at its z = Nz (halo_hi, unless upwind) and my
+        # forward-type z slot at its z = -1 (halo_lo, unless downwind)
+        to_prev = self.y[0, self._zb] if scheme != "upwind" else None
+        to_next = self.y[-1, self._zf] if scheme != "downwind" else None
+        self.halo.exchange(to_prev, to_next, self._fld_lo, self._fld_hi)
+
+    def step(self, n=1):
+        """Run n iterations; returns self."""
+        d_l21 = self.scal[0:1] if self.track_energy else None
+        d_fid = self.scal[1:2] if self.track_energy else None
+        for _ in range(n):
+            self._exchange_image_halos()
+            self.ops.cp_dual(self.pb, self._dual_input(), self.y, self.lam, self.sigma, d_l21, self._img_lo, self._img_hi, self.ws)
+            self._exchange_field_halos()
+            c2 = self.theta if self.variant == "rof" else self.sigma_A
+            self.ops.cp_primal(self.variant, self.pb, self.y, self.x, self.aux, self.x0, self.tau, c2, d_fid, self._fld_lo, self._fld_hi, self.ws)
+            self.iterations += 1
+        return self
+
+    def energy(self):
+        """0.5 |x - x0|^2 + lam L21(D u) of the last iteration over the WHOLE volume (u = the image the dual pass
+        differentiated: README.md:157).  One all-reduce of two doubles when sharded; synchronises."""
+        if not self.track_energy:
+            raise RuntimeError("energy tracking was disabled")
+        s = self.scal.clone()
+        if self.halo is not None:
+            self.halo.allreduce_sum(s)
+        l21, fid = s.tolist()
+        return 0.5 * fid + self.lam * l21
+
+    def result(self, return_pytorch_tensor=False):
+        return self.x if return_pytorch_tensor else self.x.detach().cpu().numpy()
+
+
+def cp_denoise(x0, lam, n_iter, scheme="hybrid", variant="rof", return_pytorch_tensor=False, return_energy=False, **kw):
+    """Denoise `x0` with n_iter fused Chambolle-Pock iterations; see CPSolver for the keyword arguments."""
+    solver = CPSolver(x0, lam, scheme=scheme, variant=variant, track_energy=return_energy, **kw)
+    solver.step(int(n_iter))
+    if isinstance(x0, torch.Tensor):
+        return_pytorch_tensor = True
+    out = solver.result(return_pytorch_tensor)
+    return (out, solver.energy()) if return_energy else out

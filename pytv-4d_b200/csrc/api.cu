@@ -1,0 +1,40 @@
+// libpytv_b200.so: error state, version, sizing queries.
+#include <stdarg.h>
+
+#include "host_common.cuh"
+
+namespace pytvb {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace pytvb
+
+using namespace pytvb;
+
+extern "C" {
+
+int pytvb_version(void) { return PYTVB_VERSION; }
+const char* pytvb_last_error(void) { return g_err; }
+
+int pytvb_num_components(const pytvb_problem* pb) {
+    if (check_problem(pb) != PYTVB_OK) return PYTVB_ERR_ARG;
+    return axes_of(pb).Nd;
+}
+
+size_t pytvb_reduce_workspace_bytes(const pytvb_problem* pb) {
+    if (check_problem(pb) != PYTVB_OK) return 0;
+    return (size_t)(max_partials(pb) + REDUCE_STAGE2) * sizeof(double);
+}
+
+size_t pytvb_tv_workspace_bytes(const pytvb_problem* pb) {
+    if (check_problem(pb) != PYTVB_OK) return 0;
+    const size_t es = pb->dtype == PYTVB_F32 ? 4 : 8;
+    // inverse-norm field for the slab plus one plane on each side
+    return (size_t)(pb->Nz + 2) * pb->M * pb->Ni * pb->Nj * es + 256;
+}
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+// Operator entry points: D, D_T, L21, mask.
+#include "host_common.cuh"
+
+using namespace pytvb;
+
+namespace {
+
+template <typename T> struct DArgs { ImgView<T> X; T* D; Params<T> P; int vec; cudaStream_t st; };
+template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchD {
+    static int run(const DArgs<T>& a) {
+        const Tiling tl = make_tiling(a.P.Nj, a.P.Ni, a.P.M, 0, a.P.Nz, VEC);
+        if (int rc = check_grid(tl)) return rc;
+        D_kernel<T, VEC, SCHEME, Z, TT><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.D, a.P, tl);
+        PYTVB_CUDA(cudaGetLastError());
+        return PYTVB_OK;
+    }
+};
+
+template <typename T> struct DTArgs { FieldView<T> F; T* out; Params<T> P; cudaStream_t st; };
+template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchDT {
+    static int run(const DTArgs<T>& a) {
+        const Tiling tl = make_tiling(a.P.Nj, a.P.Ni, a.P.M, 0, a.P.Nz, VEC);
+        if (int rc = check_grid(tl)) return rc;
+        DT_kernel<T, VEC, SCHEME, Z, TT><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.F, a.out, a.P, tl);
+        PYTVB_CUDA(cudaGetLastError());
+        return PYTVB_OK;
+    }
+};
+
+template <typename T>
+int run_D(const pytvb_problem* pb, const void* x, void* D, const void* lo, const void* hi, cudaStream_t st) {
+    const Axes ax = axes_of(pb);
+    DArgs<T> a;
+    a.X = ImgView<T>{(const T*)x, (const T*)lo, (const T*)hi, 1};
+    a.D = (T*)D;
+    a.P = make_params<T>(pb);
+    a.st = st;
+    const int vec = pick_vec<T>(pb, {x, D, lo, hi});
+    return dispatch<LaunchD, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
+}
+
+template <typename T>
+int run_DT(const pytvb_problem* pb, const void* p, void* out, const void* lo, const void* hi, cudaStream_t st) {
+    const Axes ax = axes_of(pb);
+    DTArgs<T> a;
+    a.F = FieldView<T>{(const T*)p, (const T*)lo, (const T*)hi};
+    a.out = (T*)out;
+    a.P = make_params<T>(pb);
+    a.st = st;
+    const int vec = pick_vec<T>(pb, {p, out, lo, hi});
+    return dispatch<LaunchDT, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
+}
+
+template <typename T>
+int run_l21(const pytvb_problem* pb, const void* D, int Nd, void* norms, double* d_sum, void* ws, cudaStream_t st) {
+    Params<T> P = make_params<T>(pb);
+    P.sZf = P.sC * Nd;
+    const int vec = pick_vec<T>(pb, {D, norms});
+    const Tiling tl = make_tiling(P.Nj, P.Ni, P.M, 0, P.Nz, vec);
+    if (int rc = check_grid(tl)) return rc;
+    double* partial = (double*)ws;
+    if (vec == 1)
+        l21_kernel<T, 1><<<(unsigned)tl.nblocks, CTA_THREADS, 0, st>>>((const T*)D, Nd, (T*)norms, partial, P, tl);
+    else
+        l21_kernel<T, VecOf<T>::value><<<(unsigned)tl.nblocks, CTA_THREADS, 0, st>>>((const T*)D, Nd, (T*)norms, partial, P, tl);
+    PYTVB_CUDA(cudaGetLastError());
+    return finalize_sum(partial, tl.nblocks, d_sum, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pytvb_D(const pytvb_problem* pb, const void* x, void* D, const void* halo_lo, const void* halo_hi, void* stream) {
+    if (int rc = check_problem(pb)) return rc;
+    PYTVB_REQUIRE(x && D, "x and D must not be NULL");
+    if (int rc = check_halos(pb, axes_of(pb).z_on, false, halo_lo, halo_hi)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    return pb->dtype == PYTVB_F32 ? run_D<float>(pb, x, D, halo_lo, halo_hi, st) : run_D<double>(pb, x, D, halo_lo, halo_hi, st);
+}
+
+int pytvb_DT(const pytvb_problem* pb, const void* p, void* out, const void* halo_lo, const void* halo_hi, void* stream) {
+    if (int rc = check_problem(pb)) return rc;
+    PYTVB_REQUIRE(p && out, "p and out must not be NULL");
+    if (int rc = check_halos(pb, axes_of(pb).z_on, true, halo_lo, halo_hi)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    return pb->dtype == PYTVB_F32 ? run_DT<float>(pb, p, out, halo_lo, halo_hi, st) : run_DT<double>(pb, p, out, halo_lo, halo_hi, st);
+}
+
+int pytvb_l21(const pytvb_problem* pb, const void* D, int64_t Nd, void* norms_or_null, double* d_sum, void* ws, void* stream) {
+    if (int rc = check_problem(pb)) return rc;
+    PYTVB_REQUIRE(D && d_sum && ws, "D, d_sum and ws must not be NULL");
+    PYTVB_REQUIRE(Nd >= 1 && Nd <= 4096, "Nd = %lld out of range", (long long)Nd);
+    cudaStream_t st = (cudaStream_t)stream;
+    return pb->dtype == PYTVB_F32 ? run_l21<float>(pb, D, (int)Nd, norms_or_null, d_sum, ws, st)
+                                  : run_l21<double>(pb, D, (int)Nd, norms_or_null, d_sum, ws, st);
+}
+
+int pytvb_apply_mask(const pytvb_problem* pb, void* x, const uint8_t* mask, int mask_is_plane, void* stream) {
+    if (int rc = check_problem(pb)) return rc;
+    PYTVB_REQUIRE(x && mask, "x and mask must not be NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long plane = (long long)pb->Ni * pb->Nj, V = plane * pb->M * pb->Nz;
+    long long nb = (V + CTA_THREADS - 1) / CTA_THREADS;
+    if (nb > 148 * 32) nb = 148 * 32;
+    if (pb->dtype == PYTVB_F32)
+        apply_mask_kernel<float><<<(unsigned)nb, CTA_THREADS, 0, st>>>((float*)x, mask, V, plane, mask_is_plane);
+    else
+        apply_mask_kernel<double><<<(unsigned)nb, CTA_THREADS, 0, st>>>((double*)x, mask, V, plane, mask_is_plane);
+    PYTVB_CUDA(cudaGetLastError());
+    return PYTVB_OK;
+}
+
+}  // extern "C"

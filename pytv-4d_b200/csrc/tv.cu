@@ -1,0 +1,67 @@
+// tv_<scheme>: TV value + sub-gradient (+ gradient norms).
+#include "host_common.cuh"
+
+using namespace pytvb;
+
+namespace {
+
+template <typename T> struct TvArgs {
+    ImgView<T> X; ImgView<T> W; T* Wz0; T* G; T* norms; double* partial; Params<T> P; int z_lo, nz; cudaStream_t st;
+    long long* nblocks_out;
+};
+
+template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchTv {
+    static int run(const TvArgs<T>& a) {
+        // sweep 1 over the slab plus the halo planes whose norms the sub-gradient reads
+        const Tiling t1 = make_tiling(a.P.Nj, a.P.Ni, a.P.M, a.z_lo, a.nz, VEC);
+        if (int rc = check_grid(t1)) return rc;
+        tv_norm_kernel<T, VEC, SCHEME, Z, TT><<<(unsigned)t1.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.Wz0, a.norms, a.partial, a.P, t1);
+        PYTVB_CUDA(cudaGetLastError());
+        *a.nblocks_out = t1.nblocks;
+        const Tiling t2 = make_tiling(a.P.Nj, a.P.Ni, a.P.M, 0, a.P.Nz, VEC);
+        tv_grad_kernel<T, VEC, SCHEME, Z, TT><<<(unsigned)t2.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.W, a.G, a.P, t2);
+        PYTVB_CUDA(cudaGetLastError());
+        return PYTVB_OK;
+    }
+};
+
+template <typename T>
+int run_tv(const pytvb_problem* pb, const void* x, void* G, void* norms, double* d_tv, const void* lo2, const void* hi2, void* ws_reduce,
+           void* ws_tv, cudaStream_t st) {
+    const Axes ax = axes_of(pb);
+    const bool has_lo = ax.z_on && pb->z_offset > 0, has_hi = ax.z_on && pb->z_offset + pb->Nz < pb->Nz_global;
+    TvArgs<T> a;
+    a.P = make_params<T>(pb);
+    a.X = ImgView<T>{(const T*)x, (const T*)lo2, (const T*)hi2, 2};
+    // inverse-norm workspace: (Nz+2) planes, plane z=-1 first; 256-byte aligned
+    uintptr_t wp = (reinterpret_cast<uintptr_t>(ws_tv) + 255) & ~uintptr_t(255);
+    T* wbuf = reinterpret_cast<T*>(wp);
+    a.Wz0 = wbuf + a.P.sZ;
+    a.W = ImgView<T>{a.Wz0, wbuf, a.Wz0 + (long long)a.P.Nz * a.P.sZ, 1};
+    a.G = (T*)G;
+    a.norms = (T*)norms;
+    a.partial = (double*)ws_reduce;
+    a.z_lo = has_lo ? -1 : 0;
+    a.nz = (int)pb->Nz + (has_lo ? 1 : 0) + (has_hi ? 1 : 0);
+    a.st = st;
+    long long nblocks = 0;
+    a.nblocks_out = &nblocks;
+    const int vec = pick_vec<T>(pb, {x, G, norms, lo2, hi2});
+    if (int rc = dispatch<LaunchTv, T>(vec, pb->scheme, ax.z_on, ax.t_on, a)) return rc;
+    return finalize_sum(a.partial, nblocks, d_tv, st);
+}
+
+}  // namespace
+
+extern "C" int pytvb_tv(const pytvb_problem* pb, const void* x, void* G, void* norms_or_null, double* d_tv, const void* halo_lo2,
+                        const void* halo_hi2, void* ws_reduce, void* ws_tv, void* stream) {
+    if (int rc = check_problem(pb)) return rc;
+    PYTVB_REQUIRE(x && G && d_tv && ws_reduce && ws_tv, "x, G, d_tv and the workspaces must not be NULL");
+    if (axes_of(pb).z_on) {
+        PYTVB_REQUIRE(!(pb->z_offset > 0 && !halo_lo2), "slab starts inside the volume: halo_lo2 (2 planes) is required");
+        PYTVB_REQUIRE(!(pb->z_offset + pb->Nz < pb->Nz_global && !halo_hi2), "slab ends inside the volume: halo_hi2 (2 planes) is required");
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    return pb->dtype == PYTVB_F32 ? run_tv<float>(pb, x, G, norms_or_null, d_tv, halo_lo2, halo_hi2, ws_reduce, ws_tv, st)
+                                  : run_tv<double>(pb, x, G, norms_or_null, d_tv, halo_lo2, halo_hi2, ws_reduce, ws_tv, st);
+}

@@ -1,0 +1,154 @@
+// TEST INFRASTRUCTURE ONLY - never linked into libpytv_b200.so.
+// Runs the per-quad device functions of pytv-4d_b200/csrc/tv_core.cuh as HOST code, quad by quad, so that
+// the index / boundary / halo / weighting logic of the CUDA kernels can be checked against the oracle in a
+// container that has no GPU.  Pointers in the problem descriptor and all arrays are HOST pointers here.
+#include <stdarg.h>
+#include <vector>
+
+#include "../../pytv-4d_b200/csrc/host_common.cuh"
+
+namespace pytvb {
+static char g_err[512];
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace pytvb
+using namespace pytvb;
+
+namespace {
+
+template <typename F>
+void for_each_quad(int z_lo, int nz, int M, int Ni, int Nj, int vec, F f) {
+    for (int z = z_lo; z < z_lo + nz; ++z)
+        for (int t = 0; t < M; ++t)
+            for (int i = 0; i < Ni; ++i)
+                for (int j0 = 0; j0 < Nj; j0 += vec) f(z, t, i, j0);
+}
+
+template <typename T> struct EArgs {
+    Params<T> P; ImgView<T> X; ImgView<T> W; FieldView<T> F; T* out; T* out2; T* aux; const T* x0; T c0, c1; int z_lo, nz; int variant; double* sum;
+};
+
+template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct ED {
+    static int run(const EArgs<T>& a) {
+        typedef Comp<SCHEME, Z, TT> C;
+        for_each_quad(0, a.P.Nz, a.P.M, a.P.Ni, a.P.Nj, VEC, [&](int z, int t, int i, int j0) {
+            T d[C::ND][VEC];
+            quad_D<T, VEC, SCHEME, Z, TT>(d, a.X, a.P, z, t, i, j0);
+            for (int k = 0; k < C::ND; ++k)
+                for (int e = 0; e < VEC; ++e)
+                    a.out[(long long)z * a.P.sZf + (long long)k * a.P.sC + (long long)t * a.P.sT + (long long)i * a.P.Nj + j0 + e] = d[k][e];
+        });
+        return 0;
+    }
+};
+template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct EDT {
+    static int run(const EArgs<T>& a) {
+        for_each_quad(0, a.P.Nz, a.P.M, a.P.Ni, a.P.Nj, VEC, [&](int z, int t, int i, int j0) {
+            T o[VEC];
+            quad_DT<T, VEC, SCHEME, Z, TT>(o, a.F, a.P, z, t, i, j0);
+            for (int e = 0; e < VEC; ++e) a.out[(long long)z * a.P.sZ + (long long)t * a.P.sT + (long long)i * a.P.Nj + j0 + e] = o[e];
+        });
+        return 0;
+    }
+};
+template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct ETV {
+    static int run(const EArgs<T>& a) {
+        typedef Comp<SCHEME, Z, TT> C;
+        T* Wz0 = const_cast<T*>(a.W.base);
+        double tv = 0;
+        for_each_quad(a.z_lo, a.nz, a.P.M, a.P.Ni, a.P.Nj, VEC, [&](int z, int t, int i, int j0) {
+            T d[C::ND][VEC], nr[VEC];
+            quad_D<T, VEC, SCHEME, Z, TT>(d, a.X, a.P, z, t, i, j0);
+            quad_norm<T, VEC, C::ND>(nr, d);
+            const long long off = (long long)z * a.P.sZ + (long long)t * a.P.sT + (long long)i * a.P.Nj + j0;
+            for (int e = 0; e < VEC; ++e) {
+                Wz0[off + e] = nr[e] > T(0) ? T(1) / nr[e] : T(0);
+                if (z >= 0 && z < a.P.Nz) {
+                    tv += (double)nr[e];
+                    if (a.out2) a.out2[off + e] = nr[e] > T(0) ? nr[e] : T(INFINITY);
+                }
+            }
+        });
+        for_each_quad(0, a.P.Nz, a.P.M, a.P.Ni, a.P.Nj, VEC, [&](int z, int t, int i, int j0) {
+            T g[VEC];
+            quad_G<T, VEC, SCHEME, Z, TT>(g, a.X, a.W, a.P, z, t, i, j0);
+            for (int e = 0; e < VEC; ++e) a.out[(long long)z * a.P.sZ + (long long)t * a.P.sT + (long long)i * a.P.Nj + j0 + e] = g[e];
+        });
+        *a.sum = tv;
+        return 0;
+    }
+};
+template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct EDual {
+    static int run(const EArgs<T>& a) {
+        double s = 0;
+        for_each_quad(0, a.P.Nz, a.P.M, a.P.Ni, a.P.Nj, VEC, [&](int z, int t, int i, int j0) {
+            s += (double)quad_cp_dual<T, VEC, SCHEME, Z, TT>(a.out, a.X, a.P, a.c0, a.c1, z, t, i, j0);
+        });
+        *a.sum = s;
+        return 0;
+    }
+};
+template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct EPrimal {
+    static int run(const EArgs<T>& a) {
+        double s = 0;
+        for_each_quad(0, a.P.Nz, a.P.M, a.P.Ni, a.P.Nj, VEC, [&](int z, int t, int i, int j0) {
+            if (a.variant == 0)
+                s += (double)quad_cp_primal_rof<T, VEC, SCHEME, Z, TT>(a.out, a.aux, a.x0, a.F, a.P, a.c0, a.c1, z, t, i, j0);
+            else
+                s += (double)quad_cp_primal_readme<T, VEC, SCHEME, Z, TT>(a.out, a.aux, a.x0, a.F, a.P, a.c0, a.c1, z, t, i, j0);
+        });
+        *a.sum = s;
+        return 0;
+    }
+};
+
+template <typename T> int vec_for(const pytvb_problem* pb, int force_scalar) {
+    return (force_scalar || pb->Nj % VecOf<T>::value) ? 1 : VecOf<T>::value;
+}
+
+template <typename T>
+int run(int op, const pytvb_problem* pb, const void* in, void* out, void* out2, void* aux, const void* x0, const void* lo, const void* hi,
+        double c0, double c1, int variant, int force_scalar, double* sum) {
+    const Axes ax = axes_of(pb);
+    EArgs<T> a;
+    a.P = make_params<T>(pb);
+    a.out = (T*)out; a.out2 = (T*)out2; a.aux = (T*)aux; a.x0 = (const T*)x0; a.c0 = (T)c0; a.c1 = (T)c1; a.variant = variant; a.sum = sum;
+    a.z_lo = 0; a.nz = a.P.Nz;
+    const int vec = vec_for<T>(pb, force_scalar);
+    std::vector<T> wbuf;
+    switch (op) {
+        case 0: a.X = ImgView<T>{(const T*)in, (const T*)lo, (const T*)hi, 1}; return dispatch<ED, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
+        case 1: a.F = FieldView<T>{(const T*)in, (const T*)lo, (const T*)hi}; return dispatch<EDT, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
+        case 2: {
+            const bool has_lo = ax.z_on && pb->z_offset > 0, has_hi = ax.z_on && pb->z_offset + pb->Nz < pb->Nz_global;
+            a.X = ImgView<T>{(const T*)in, (const T*)lo, (const T*)hi, 2};
+            wbuf.assign((size_t)(a.P.Nz + 2) * a.P.sZ, T(0));
+            T* Wz0 = wbuf.data() + a.P.sZ;
+            a.W = ImgView<T>{Wz0, wbuf.data(), Wz0 + (long long)a.P.Nz * a.P.sZ, 1};
+            a.z_lo = has_lo ? -1 : 0;
+            a.nz = a.P.Nz + (has_lo ? 1 : 0) + (has_hi ? 1 : 0);
+            return dispatch<ETV, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
+        }
+        case 3: a.X = ImgView<T>{(const T*)in, (const T*)lo, (const T*)hi, 1}; return dispatch<EDual, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
+        case 4: a.F = FieldView<T>{(const T*)in, (const T*)lo, (const T*)hi}; return dispatch<EPrimal, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
+    }
+    return -1;
+}
+
+}  // namespace
+
+// op: 0 D (in=x, out=D) | 1 DT (in=p, out=img) | 2 tv (in=x, out=G, out2=norms|NULL, sum=tv)
+//     3 cp_dual (in=xbar, out=y in place, c0=sigma, c1=1/lam, sum=l21) | 4 cp_primal (in=y, out=x, aux, x0, c0=tau, c1=theta|sigma_A, variant)
+extern "C" int pytvb_emulate(int op, const pytvb_problem* pb, const void* in, void* out, void* out2, void* aux, const void* x0, const void* lo,
+                             const void* hi, double c0, double c1, int variant, int force_scalar, double* sum) {
+    if (check_problem(pb)) return -1;
+    double dummy = 0;
+    if (!sum) sum = &dummy;
+    return pb->dtype == PYTVB_F32 ? run<float>(op, pb, in, out, out2, aux, x0, lo, hi, c0, c1, variant, force_scalar, sum)
+                                  : run<double>(op, pb, in, out, out2, aux, x0, lo, hi, c0, c1, variant, force_scalar, sum);
+}
+extern "C" const char* pytvb_emulate_error(void) { return g_err; }

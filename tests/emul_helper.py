@@ -1,0 +1,138 @@
+"""Loader for the host emulation of the CUDA per-quad code (tests/emul/emul.cu).  Test infrastructure."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMUL_DIR = os.path.join(ROOT, "tests", "emul")
+EMUL_SO = os.path.join(EMUL_DIR, "libpytvb_emul.so")
+sys.path.insert(0, ROOT)
+
+import pytv_b200  # noqa: E402
+from pytv_b200 import _lib  # noqa: E402
+
+
+def build_emul(force=False):
+    src = os.path.join(EMUL_DIR, "emul.cu")
+    deps = [src] + [os.path.join(ROOT, "pytv-4d_b200", "csrc", f) for f in ("tv_core.cuh", "kernels.cuh", "host_common.cuh")]
+    if not force and os.path.exists(EMUL_SO) and all(os.path.getmtime(EMUL_SO) >= os.path.getmtime(d) for d in deps):
+        return EMUL_SO
+    cmd = ["nvcc", "-O1", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "--extended-lambda", "-gencode",
+           "arch=compute_100a,code=sm_100a", src, "-o", EMUL_SO]
+    subprocess.run(cmd, check=True, cwd=EMUL_DIR)
+    return EMUL_SO
+
+
+_h = None
+
+
+def emul():
+    global _h
+    if _h is None:
+        _h = ctypes.CDLL(build_emul())
+        VP = ctypes.c_void_p
+        _h.pytvb_emulate.restype = ctypes.c_int
+        _h.pytvb_emulate.argtypes = [ctypes.c_int, ctypes.POINTER(_lib.Problem), VP, VP, VP, VP, VP, VP, VP, ctypes.c_double, ctypes.c_double,
+                                     ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    return _h
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _problem(scheme, x_dtype, shape, rz, rt, mask_static, fac, z_offset=0, Nz_global=None):
+    ms = None
+    if not isinstance(mask_static, bool) and mask_static is not None:
+        ms = np.ascontiguousarray(np.asarray(mask_static).reshape(shape[-2], shape[-1]).astype(np.uint8))
+    pb = _lib.make_problem(scheme, _lib.F32 if x_dtype == np.float32 else _lib.F64, shape, rz, rt, fac,
+                           ms.ctypes.data if ms is not None else None, z_offset, Nz_global)
+    return pb, ms
+
+
+def _call(op, pb, inp, out, out2=None, aux=None, x0=None, lo=None, hi=None, c0=0.0, c1=0.0, variant=0, scalar=False):
+    s = ctypes.c_double(0.0)
+    rc = emul().pytvb_emulate(op, ctypes.byref(pb), _ptr(inp), _ptr(out), _ptr(out2), _ptr(aux), _ptr(x0), _ptr(lo), _ptr(hi), c0, c1, variant,
+                              int(scalar), ctypes.byref(s))
+    assert rc == 0, emul().pytvb_emulate_error()
+    return s.value
+
+
+def nd_of(pb):
+    z_on = pb.Nz_global > 1 and pb.reg_z_over_reg > 0
+    t_on = pb.M > 1 and pb.reg_time > 0
+    return (4 + 2 * z_on + 2 * t_on) if pb.scheme == 3 else (2 + z_on + t_on)
+
+
+def D(x, scheme, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_reg_static=0.0, lo=None, hi=None, z_offset=0, Nz_global=None,
+      scalar=False):
+    x = np.ascontiguousarray(x)
+    pb, keep = _problem(scheme, x.dtype, x.shape, reg_z_over_reg, reg_time, mask_static, factor_reg_static, z_offset, Nz_global)
+    out = np.full((x.shape[0], nd_of(pb)) + x.shape[1:], np.nan, dtype=x.dtype)
+    _call(0, pb, x, out, lo=lo, hi=hi, scalar=scalar)
+    return out
+
+
+def D_T(p, scheme, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_reg_static=0.0, lo=None, hi=None, z_offset=0, Nz_global=None,
+        scalar=False):
+    p = np.ascontiguousarray(p)
+    shape = (p.shape[0],) + p.shape[2:]
+    pb, keep = _problem(scheme, p.dtype, shape, reg_z_over_reg, reg_time, mask_static, factor_reg_static, z_offset, Nz_global)
+    assert nd_of(pb) == p.shape[1]
+    out = np.full(shape, np.nan, dtype=p.dtype)
+    _call(1, pb, p, out, lo=lo, hi=hi, scalar=scalar)
+    return out
+
+
+def tv(x, scheme, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_reg_static=0.0, lo=None, hi=None, z_offset=0, Nz_global=None,
+       scalar=False):
+    x = np.ascontiguousarray(x)
+    pb, keep = _problem(scheme, x.dtype, x.shape, reg_z_over_reg, reg_time, mask_static, factor_reg_static, z_offset, Nz_global)
+    G = np.full(x.shape, np.nan, dtype=x.dtype)
+    norms = np.full(x.shape, np.nan, dtype=x.dtype)
+    val = _call(2, pb, x, G, out2=norms, lo=lo, hi=hi, scalar=scalar)
+    return val, G, norms
+
+
+def cp_dual(xbar, y, scheme, lam, sigma, lo=None, hi=None, z_offset=0, Nz_global=None, scalar=False, **w):
+    pb, keep = _problem(scheme, xbar.dtype, xbar.shape, w.get("reg_z_over_reg", 1.0), w.get("reg_time", 0.0), w.get("mask_static", False),
+                        w.get("factor_reg_static", 0.0), z_offset, Nz_global)
+    return _call(3, pb, np.ascontiguousarray(xbar), y, lo=lo, hi=hi, c0=sigma, c1=1.0 / lam, scalar=scalar)
+
+
+def cp_primal(y, x, aux, x0, scheme, tau, c2, variant, lo=None, hi=None, z_offset=0, Nz_global=None, scalar=False, **w):
+    pb, keep = _problem(scheme, x.dtype, x.shape, w.get("reg_z_over_reg", 1.0), w.get("reg_time", 0.0), w.get("mask_static", False),
+                        w.get("factor_reg_static", 0.0), z_offset, Nz_global)
+    return _call(4, pb, np.ascontiguousarray(y), x, aux=aux, x0=x0, lo=lo, hi=hi, c0=tau, c1=c2, variant=variant, scalar=scalar)
+
+
+class EmulOps:
+    """Executor for pytv_b200.cp.CPSolver that runs the per-quad CUDA code on the host (CPU tensors).
+    Lets the multi-rank slab / halo / all-reduce logic be tested with the gloo backend."""
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+    def cp_dual(self, pb, xbar, y, lam, sigma, d_l21, lo, hi, ws):
+        s = ctypes.c_double(0.0)
+        rc = emul().pytvb_emulate(3, ctypes.byref(pb), self._p(xbar), self._p(y), None, None, None, self._p(lo), self._p(hi), sigma, 1.0 / lam, 0, 0,
+                                  ctypes.byref(s))
+        assert rc == 0
+        if d_l21 is not None:
+            d_l21[0] = s.value
+
+    def cp_primal(self, variant, pb, y, x, aux, x0, tau, c2, d_fid, lo, hi, ws):
+        s = ctypes.c_double(0.0)
+        rc = emul().pytvb_emulate(4, ctypes.byref(pb), self._p(y), self._p(x), None, self._p(aux), self._p(x0), self._p(lo), self._p(hi), tau, c2,
+                                  0 if variant == "rof" else 1, 0, ctypes.byref(s))
+        assert rc == 0
+        if d_fid is not None:
+            d_fid[0] = s.value
+
+    def workspace(self, pb, device):
+        import torch
+        return torch.empty(1, dtype=torch.uint8)

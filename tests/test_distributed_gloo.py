@@ -1,0 +1,85 @@
+"""world_size-2 (and 3) runs of the slab-sharded Chambolle-Pock solver over the gloo backend on CPU.
+The per-pass arithmetic is the CUDA per-quad code executed on the host (tests/emul); what is under test is
+the N>1 host logic of pytv_b200.cp: slab placement, which planes go to which neighbour, halo buffers, the
+energy all-reduce.  The result must equal the single-domain oracle."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, scheme, variant, Nz, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import emul_helper as em
+    import pytv_b200
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rs = np.random.RandomState(17)
+        M, N = 2, 8
+        x0 = rs.rand(Nz, M, N, N)
+        ms = rs.rand(1, 1, N, N) > 0.5
+        off, cnt = pytv_b200.partition_z(Nz, world)[rank]
+        solver = pytv_b200.CPSolver(x0[off:off + cnt], lam=0.15, scheme=scheme, variant=variant, reg_z_over_reg=0.5, reg_time=0.25,
+                                    mask_static=ms, factor_reg_static=2.0, distributed=True, ops=em.EmulOps())
+        assert solver.z_offset == off and solver.Nz_global == Nz
+        energies = []
+        for _ in range(4):
+            solver.step()
+            energies.append(solver.energy())
+        np.save(os.path.join(out_dir, "x_%d.npy" % rank), solver.result())
+        np.save(os.path.join(out_dir, "y_%d.npy" % rank), solver.y.numpy())
+        if rank == 0:
+            np.save(os.path.join(out_dir, "energies.npy"), np.array(energies))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("variant", ["rof", "readme"])
+@pytest.mark.parametrize("scheme,world,Nz", [("hybrid", 2, 5), ("upwind", 2, 4), ("downwind", 2, 4), ("central", 2, 6), ("hybrid", 3, 7)])
+def test_sharded_cp_equals_single_domain(tmp_path, scheme, world, Nz, variant):
+    from oracle import tv_oracle as orc
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, scheme, variant, Nz, str(tmp_path)), nprocs=world, join=True)
+    x = np.concatenate([np.load(tmp_path / ("x_%d.npy" % r)) for r in range(world)], axis=0)
+    y = np.concatenate([np.load(tmp_path / ("y_%d.npy" % r)) for r in range(world)], axis=0)
+    energies = np.load(tmp_path / "energies.npy")
+    rs = np.random.RandomState(17)
+    M, N = 2, 8
+    x0 = rs.rand(Nz, M, N, N)
+    ms = rs.rand(1, 1, N, N) > 0.5
+    kw = dict(reg_z_over_reg=0.5, reg_time=0.25, mask_static=ms, factor_reg_static=2.0)
+    Nd = orc.num_components(scheme, Nz, M, 0.5, 0.25)
+    L2 = (1.0 if scheme == "central" else 4.0) * (2 + 0.5 + 0.25 * 2.0)
+    tau = 1.0 / (L2 + 1.0)
+    ref_e = []
+    if variant == "rof":
+        xr, xb, yr = x0.copy(), x0.copy(), np.zeros((Nz, Nd, M, N, N))
+        for _ in range(4):
+            xr, xb, yr, e = orc.cp_rof_step(xr, xb, x0, yr, scheme, lam=0.15, sigma=0.5, tau=tau, theta=1.0, **kw)
+            ref_e.append(e)
+    else:
+        xr, yf, yr = x0.copy(), np.zeros_like(x0), np.zeros((Nz, Nd, M, N, N))
+        for _ in range(4):
+            xr, yf, yr, e = orc.cp_readme_step(xr, x0, yf, yr, scheme, lam=0.15, sigma_D=0.5, sigma_A=1.0, tau=tau, **kw)
+            ref_e.append(e)
+    np.testing.assert_allclose(x, xr, atol=1e-13)
+    np.testing.assert_allclose(y, yr, atol=1e-13)
+    np.testing.assert_allclose(energies, ref_e, rtol=1e-12)

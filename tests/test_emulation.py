@@ -1,0 +1,190 @@
+"""The per-quad CUDA code (pytv-4d_b200/csrc/tv_core.cuh), executed on the host quad by quad, against the
+oracle and the reference goldens.  This pins the index / boundary / halo / weight logic of the kernels
+without a GPU; the -m gpu tests then check the same functions through the real launches."""
+import numpy as np
+import pytest
+
+import cases
+import emul_helper as em
+from oracle import tv_oracle as orc
+
+SCHEMES = cases.SCHEMES
+
+
+def _tol(dtype):
+    return dict(rtol=0, atol=1e-12) if dtype == np.float64 else dict(rtol=0, atol=1e-5)
+
+
+@pytest.mark.parametrize("scalar", [False, True], ids=["vec", "scalar"])
+@pytest.mark.parametrize("case", [pytest.param(c, id=c["key"]) for c in cases.small_cases()])
+def test_operators_match_reference_goldens(case, scalar, golden_small):
+    key, scheme = case["key"], case["scheme"]
+    kw = cases.weight_kwargs(case)
+    x = cases.make_image(case)
+    gD = golden_small[key + "/D"]
+    np.testing.assert_allclose(em.D(x, scheme, scalar=scalar, **kw), gD, rtol=0, atol=1e-13)
+    p = cases.make_field(case, gD.shape)
+    np.testing.assert_allclose(em.D_T(p, scheme, scalar=scalar, **kw), golden_small[key + "/DT"], rtol=0, atol=1e-11)
+    tv, G, norms = em.tv(x, scheme, scalar=scalar, **kw)
+    assert tv == pytest.approx(float(golden_small[key + "/tv"]), rel=1e-13)
+    np.testing.assert_allclose(G, golden_small[key + "/G"], rtol=0, atol=1e-10)
+    gn = golden_small[key + "/norms"]
+    assert np.array_equal(np.isinf(norms), np.isinf(gn))
+    np.testing.assert_allclose(norms[np.isfinite(gn)], gn[np.isfinite(gn)], rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("case", [pytest.param(c, id=c["key"]) for c in cases.small_cases() if c["wname"] in ("default", "ztmask")])
+def test_float32_within_north_star_tolerance(case, golden_small):
+    key, scheme = case["key"], case["scheme"]
+    kw = cases.weight_kwargs(case)
+    x = cases.make_image(case, np.float32)
+    gD = golden_small[key + "/D"]
+    np.testing.assert_allclose(em.D(x, scheme, **kw), gD, rtol=0, atol=1e-5)
+    p = cases.make_field(case, gD.shape, np.float32)
+    np.testing.assert_allclose(em.D_T(p, scheme, **kw), golden_small[key + "/DT"], rtol=0, atol=1e-5)
+    tv, G, norms = em.tv(x, scheme, **kw)
+    assert tv == pytest.approx(float(golden_small[key + "/tv"]), rel=1e-5)
+    # against the float32 oracle the sub-gradient agrees to a few ulp even where norms are tiny
+    _, G32 = orc.tv(x.copy(), scheme, **kw)
+    np.testing.assert_allclose(G, G32, rtol=0, atol=5e-4)
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("split", [(2, 5), (1, 3, 4), (3,)], ids=["3slabs", "4slabs", "2slabs"])
+def test_slabs_with_halos_reproduce_whole_volume(scheme, split):
+    """Nz-slab decomposition: every slab, given its halo planes, reproduces its part of the
+    whole-volume result exactly."""
+    rs = np.random.RandomState(21)
+    Nz, M, N = 6, 3, 8
+    x = rs.rand(Nz, M, N, N)
+    x[..., :2, :3] = 0.5
+    ms = rs.rand(1, 1, N, N) > 0.5
+    kw = dict(reg_z_over_reg=0.7, reg_time=0.3, mask_static=ms, factor_reg_static=2.0)
+    Dx = orc.D(x, scheme, **kw)
+    p = rs.randn(*Dx.shape)
+    DTp = orc.D_T(p, scheme, **kw)
+    tv, G, norms = orc.tv(x.copy(), scheme, return_grad_norms=True, **kw)
+    zf = {"upwind": 2, "downwind": 2, "central": 2, "hybrid": 4}[scheme]   # forward-type z slot
+    zb = {"upwind": 2, "downwind": 2, "central": 2, "hybrid": 5}[scheme]   # backward-type z slot
+    bounds = [0] + list(split) + [Nz]
+    tv_sum = 0.0
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        xs = np.ascontiguousarray(x[a:b])
+        lo = np.ascontiguousarray(x[a - 1]) if a > 0 else None
+        hi = np.ascontiguousarray(x[b]) if b < Nz else None
+        np.testing.assert_allclose(em.D(xs, scheme, lo=lo, hi=hi, z_offset=a, Nz_global=Nz, **kw), Dx[a:b], atol=1e-14)
+        plo = np.ascontiguousarray(p[a - 1, zf]) if a > 0 else None
+        phi = np.ascontiguousarray(p[b, zb]) if b < Nz else None
+        np.testing.assert_allclose(em.D_T(np.ascontiguousarray(p[a:b]), scheme, lo=plo, hi=phi, z_offset=a, Nz_global=Nz, **kw), DTp[a:b], atol=1e-13)
+        # 2-plane halos for tv; planes outside the volume are never read, fill them with NaN to prove it
+        lo2 = np.full((2, M, N, N), np.nan)
+        hi2 = np.full((2, M, N, N), np.nan)
+        for k in (1, 2):
+            if a - k >= 0:
+                lo2[2 - k] = x[a - k]
+            if b + k - 1 < Nz:
+                hi2[k - 1] = x[b + k - 1]
+        tvs, Gs, ns = em.tv(xs, scheme, lo=lo2 if a > 0 else None, hi=hi2 if b < Nz else None, z_offset=a, Nz_global=Nz, **kw)
+        np.testing.assert_allclose(Gs, G[a:b], atol=1e-12)
+        np.testing.assert_allclose(ns, norms[a:b], atol=1e-13)
+        tv_sum += tvs
+    assert tv_sum == pytest.approx(tv, rel=1e-13)
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+def test_cp_iterations_match_oracle(scheme, dtype, golden_kat):
+    g = golden_kat["cp_small4d"][scheme]
+    x0 = cases.cp_volume().astype(dtype)
+    kw = dict(reg_z_over_reg=0.5, reg_time=2 ** -5, mask_static=cases.cp_mask_static(), factor_reg_static=4.0)
+    Nd = orc.num_components(scheme, 4, 3, 0.5, 2 ** -5)
+    lam, sigma, tau = 0.2, 0.5, 1.0 / 17.0
+    rel = 1e-12 if dtype == np.float64 else 2e-5
+    # README form
+    x, y_f, y = x0.copy(), np.zeros_like(x0), np.zeros((4, Nd, 3, 8, 8), dtype)
+    losses = []
+    for _ in range(10):
+        l21 = em.cp_dual(x, y, scheme, lam, sigma, **kw)
+        fid = em.cp_primal(y, x, y_f, x0, scheme, tau, 1.0, 1, **kw)
+        losses.append(0.5 * fid + lam * l21)
+    np.testing.assert_allclose(losses, g["readme_losses"], rtol=rel)
+    assert x.sum(dtype=np.float64) == pytest.approx(g["readme_sum_x"], rel=rel)
+    assert np.abs(y).sum(dtype=np.float64) == pytest.approx(g["readme_sum_abs_y"], rel=10 * rel)
+    # ROF form
+    x, xbar, y = x0.copy(), x0.copy(), np.zeros((4, Nd, 3, 8, 8), dtype)
+    energies = []
+    for _ in range(10):
+        l21 = em.cp_dual(xbar, y, scheme, lam, sigma, **kw)
+        fid = em.cp_primal(y, x, xbar, x0, scheme, tau, 1.0, 0, **kw)
+        energies.append(0.5 * fid + lam * l21)
+    np.testing.assert_allclose(energies, g["rof_energies"], rtol=rel)
+    assert x.sum(dtype=np.float64) == pytest.approx(g["rof_sum_x"], rel=rel)
+    assert xbar.sum(dtype=np.float64) == pytest.approx(g["rof_sum_xbar"], rel=rel)
+    assert x[1, 1, 3, 4] == pytest.approx(g["rof_x_probe"], rel=1e-11 if dtype == np.float64 else 1e-4)
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_cp_slabs(scheme):
+    """One CP iteration computed slab by slab with halos equals the whole-volume iteration."""
+    rs = np.random.RandomState(4)
+    Nz, M, N = 5, 2, 8
+    x0 = rs.rand(Nz, M, N, N)
+    kw = dict(reg_z_over_reg=0.5, reg_time=0.25)
+    Nd = orc.num_components(scheme, Nz, M, 0.5, 0.25)
+    y = 0.05 * rs.randn(Nz, Nd, M, N, N)
+    x = x0 + 0.1 * rs.randn(*x0.shape)
+    xbar = x + 0.01 * rs.randn(*x0.shape)
+    x_ref, xbar_ref, y_ref, e_ref = orc.cp_rof_step(x.copy(), xbar.copy(), x0, y.copy(), scheme, lam=0.1, sigma=0.5, tau=0.07, theta=0.9, **kw)
+    zf = 4 if scheme == "hybrid" else 2
+    zb = 5 if scheme == "hybrid" else 2
+    cut = 2
+    y_new = y.copy()
+    l21 = 0.0
+    for a, b in ((0, cut), (cut, Nz)):
+        ys = np.ascontiguousarray(y_new[a:b])
+        lo = np.ascontiguousarray(xbar[a - 1]) if a > 0 else None
+        hi = np.ascontiguousarray(xbar[b]) if b < Nz else None
+        l21 += em.cp_dual(np.ascontiguousarray(xbar[a:b]), ys, scheme, 0.1, 0.5, lo=lo, hi=hi, z_offset=a, Nz_global=Nz, **kw)
+        y_new[a:b] = ys
+    np.testing.assert_allclose(y_new, y_ref, atol=1e-13)
+    x_new, xbar_new = x.copy(), xbar.copy()
+    fid = 0.0
+    for a, b in ((0, cut), (cut, Nz)):
+        xs, xbs = np.ascontiguousarray(x_new[a:b]), np.ascontiguousarray(xbar_new[a:b])
+        plo = np.ascontiguousarray(y_new[a - 1, zf]) if a > 0 else None
+        phi = np.ascontiguousarray(y_new[b, zb]) if b < Nz else None
+        fid += em.cp_primal(np.ascontiguousarray(y_new[a:b]), xs, xbs, np.ascontiguousarray(x0[a:b]), scheme, 0.07, 0.9, 0, lo=plo, hi=phi,
+                            z_offset=a, Nz_global=Nz, **kw)
+        x_new[a:b], xbar_new[a:b] = xs, xbs
+    np.testing.assert_allclose(x_new, x_ref, atol=1e-13)
+    np.testing.assert_allclose(xbar_new, xbar_ref, atol=1e-13)
+    assert 0.5 * fid + 0.1 * l21 == pytest.approx(e_ref, rel=1e-12)
+
+
+def test_central_nz2_intent():
+    rs = np.random.RandomState(9)
+    x = rs.rand(2, 2, 6, 6)
+    for kw in (dict(), dict(reg_time=0.5)):
+        np.testing.assert_allclose(em.D(x, "central", **kw), orc.D(x, "central", **kw), atol=1e-14)
+        p = rs.randn(*orc.D(x, "central", **kw).shape)
+        np.testing.assert_allclose(em.D_T(p, "central", **kw), orc.D_T(p, "central", **kw), atol=1e-13)
+        tv, G, _ = em.tv(x, "central", **kw)
+        tvo, Go = orc.tv(x.copy(), "central", **kw)
+        assert tv == pytest.approx(tvo, rel=1e-13)
+        np.testing.assert_allclose(G, Go, atol=1e-12)
+
+
+def test_non_square_images():
+    """The kernels take Ni and Nj separately (reference: square only, README.md:259)."""
+    rs = np.random.RandomState(13)
+    x = rs.rand(3, 2, 5, 12)
+    for scheme in SCHEMES:
+        kw = dict(reg_time=0.5)
+        Dx = orc.D(x, scheme, **kw)
+        np.testing.assert_allclose(em.D(x, scheme, **kw), Dx, atol=1e-14)
+        p = rs.randn(*Dx.shape)
+        np.testing.assert_allclose(em.D_T(p, scheme, **kw), orc.D_T(p, scheme, **kw), atol=1e-13)
+        tv, G, _ = em.tv(x, scheme, **kw)
+        tvo, Go = orc.tv(x.copy(), scheme, **kw)
+        assert tv == pytest.approx(tvo, rel=1e-13)
+        np.testing.assert_allclose(G, Go, atol=1e-12)
