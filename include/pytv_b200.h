@@ -56,6 +56,8 @@ typedef struct pytvb_problem {
 
 int pytvb_version(void);
 const char* pytvb_last_error(void);
+/* Number of CUDA kernels this library has launched in the calling process (diagnostics / benchmarks). */
+uint64_t pytvb_launch_count(void);
 
 /* Number of difference components Nd (tv_operators_CPU.py:110-114 hybrid: 4/6/8; :256-260 others: 2/3/4). */
 int pytvb_num_components(const pytvb_problem* pb);

@@ -46,6 +46,7 @@ _PB = ctypes.POINTER(Problem)
 _PROTOTYPES = {
     "pytvb_version": (ctypes.c_int, []),
     "pytvb_last_error": (ctypes.c_char_p, []),
+    "pytvb_launch_count": (ctypes.c_uint64, []),
     "pytvb_num_components": (ctypes.c_int, [_PB]),
     "pytvb_reduce_workspace_bytes": (ctypes.c_size_t, [_PB]),
     "pytvb_tv_workspace_bytes": (ctypes.c_size_t, [_PB]),

@@ -224,6 +224,18 @@ class CPSolver:
             self.iterations += 1
         return self
 
+    def step_host(self, x0_host, x_out_host=None):
+        """One iteration against HOST-resident data: upload `x0_host` (numpy array or CPU tensor; pinned memory
+        gives full PCIe speed) as the data term, iterate once, download the current x into `x_out_host`, return
+        the energy.  State (x, xbar | y_f, y) stays on the device.  Synchronises."""
+        src = x0_host if isinstance(x0_host, torch.Tensor) else torch.from_numpy(x0_host)
+        self.x0.copy_(src, non_blocking=True)
+        self.step(1)
+        if x_out_host is not None:
+            dst = x_out_host if isinstance(x_out_host, torch.Tensor) else torch.from_numpy(x_out_host)
+            dst.copy_(self.x, non_blocking=True)
+        return self.energy()
+
     def energy(self):
         """0.5 |x - x0|^2 + lam L21(D u) of the last iteration over the WHOLE volume (u = the image the dual pass
         differentiated: README.md:157).  One all-reduce of two doubles when sharded; synchronises."""

@@ -1,6 +1,8 @@
 // libpytv_b200.so: error state, version, sizing queries.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "host_common.cuh"
 
 namespace pytvb {
@@ -11,6 +13,8 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+static std::atomic<unsigned long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 }  // namespace pytvb
 
 using namespace pytvb;
@@ -19,6 +23,7 @@ extern "C" {
 
 int pytvb_version(void) { return PYTVB_VERSION; }
 const char* pytvb_last_error(void) { return g_err; }
+uint64_t pytvb_launch_count(void) { return (uint64_t)g_launches.load(std::memory_order_relaxed); }
 
 int pytvb_num_components(const pytvb_problem* pb) {
     if (check_problem(pb) != PYTVB_OK) return PYTVB_ERR_ARG;

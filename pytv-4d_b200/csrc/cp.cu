@@ -11,6 +11,7 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchDual {
         const Tiling tl = make_tiling(a.P.Nj, a.P.Ni, a.P.M, 0, a.P.Nz, VEC);
         if (int rc = check_grid(tl)) return rc;
         cp_dual_kernel<T, VEC, SCHEME, Z, TT><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.Xb, a.y, a.partial, a.P, a.sigma, a.inv_lam, tl);
+        count_launches(1);
         PYTVB_CUDA(cudaGetLastError());
         *a.nb = tl.nblocks;
         return PYTVB_OK;
@@ -28,6 +29,7 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchPrimal 
             cp_primal_kernel<T, VEC, SCHEME, Z, TT, 0><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.Y, a.x, a.aux, a.x0, a.partial, a.P, a.tau, a.c2, tl);
         else
             cp_primal_kernel<T, VEC, SCHEME, Z, TT, 1><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.Y, a.x, a.aux, a.x0, a.partial, a.P, a.tau, a.c2, tl);
+        count_launches(1);
         PYTVB_CUDA(cudaGetLastError());
         *a.nb = tl.nblocks;
         return PYTVB_OK;

@@ -12,6 +12,7 @@
 namespace pytvb {
 
 void set_error(const char* fmt, ...);   // api.cu
+void count_launches(int n);             // api.cu: kernels launched by this library (pytvb_launch_count)
 
 #define PYTVB_CUDA(call)                                                                              \
     do {                                                                                              \
@@ -143,10 +144,12 @@ inline long long max_partials(const pytvb_problem* pb) {
 inline int finalize_sum(double* partials, long long n, double* d_out, cudaStream_t st) {
     if (n <= 8192) {
         reduce_chunks_kernel<<<1, CTA_THREADS, 0, st>>>(partials, n, d_out, 1.0);
+        count_launches(1);
     } else {
         double* stage2 = partials + n;
         reduce_chunks_kernel<<<REDUCE_STAGE2, CTA_THREADS, 0, st>>>(partials, n, stage2, 1.0);
         reduce_chunks_kernel<<<1, CTA_THREADS, 0, st>>>(stage2, REDUCE_STAGE2, d_out, 1.0);
+        count_launches(2);
     }
     PYTVB_CUDA(cudaGetLastError());
     return PYTVB_OK;

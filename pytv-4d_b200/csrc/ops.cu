@@ -11,6 +11,7 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchD {
         const Tiling tl = make_tiling(a.P.Nj, a.P.Ni, a.P.M, 0, a.P.Nz, VEC);
         if (int rc = check_grid(tl)) return rc;
         D_kernel<T, VEC, SCHEME, Z, TT><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.D, a.P, tl);
+        count_launches(1);
         PYTVB_CUDA(cudaGetLastError());
         return PYTVB_OK;
     }
@@ -22,6 +23,7 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchDT {
         const Tiling tl = make_tiling(a.P.Nj, a.P.Ni, a.P.M, 0, a.P.Nz, VEC);
         if (int rc = check_grid(tl)) return rc;
         DT_kernel<T, VEC, SCHEME, Z, TT><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.F, a.out, a.P, tl);
+        count_launches(1);
         PYTVB_CUDA(cudaGetLastError());
         return PYTVB_OK;
     }
@@ -63,6 +65,7 @@ int run_l21(const pytvb_problem* pb, const void* D, int Nd, void* norms, double*
         l21_kernel<T, 1><<<(unsigned)tl.nblocks, CTA_THREADS, 0, st>>>((const T*)D, Nd, (T*)norms, partial, P, tl);
     else
         l21_kernel<T, VecOf<T>::value><<<(unsigned)tl.nblocks, CTA_THREADS, 0, st>>>((const T*)D, Nd, (T*)norms, partial, P, tl);
+    count_launches(1);
     PYTVB_CUDA(cudaGetLastError());
     return finalize_sum(partial, tl.nblocks, d_sum, st);
 }
@@ -107,6 +110,7 @@ int pytvb_apply_mask(const pytvb_problem* pb, void* x, const uint8_t* mask, int 
         apply_mask_kernel<float><<<(unsigned)nb, CTA_THREADS, 0, st>>>((float*)x, mask, V, plane, mask_is_plane);
     else
         apply_mask_kernel<double><<<(unsigned)nb, CTA_THREADS, 0, st>>>((double*)x, mask, V, plane, mask_is_plane);
+    count_launches(1);
     PYTVB_CUDA(cudaGetLastError());
     return PYTVB_OK;
 }

@@ -16,10 +16,12 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchTv {
         const Tiling t1 = make_tiling(a.P.Nj, a.P.Ni, a.P.M, a.z_lo, a.nz, VEC);
         if (int rc = check_grid(t1)) return rc;
         tv_norm_kernel<T, VEC, SCHEME, Z, TT><<<(unsigned)t1.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.Wz0, a.norms, a.partial, a.P, t1);
+        count_launches(1);
         PYTVB_CUDA(cudaGetLastError());
         *a.nblocks_out = t1.nblocks;
         const Tiling t2 = make_tiling(a.P.Nj, a.P.Ni, a.P.M, 0, a.P.Nz, VEC);
         tv_grad_kernel<T, VEC, SCHEME, Z, TT><<<(unsigned)t2.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.W, a.G, a.P, t2);
+        count_launches(1);
         PYTVB_CUDA(cudaGetLastError());
         return PYTVB_OK;
     }

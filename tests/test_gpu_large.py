@@ -1,0 +1,128 @@
+"""Size-independent properties at BASELINE.json's full per-GPU sizes (the oracle would need minutes and
+> 100 GB there): adjointness, TV == L21(D x), scale laws, zero on constants, and slab-split equality of a
+whole Chambolle-Pock iteration.  float32, one B200."""
+import ctypes
+
+import pytest
+import torch
+
+import pytv_b200 as pytv
+from pytv_b200 import _dev, _lib
+
+pytestmark = pytest.mark.gpu
+opG, tvG = pytv.tv_operators_GPU, pytv.tv_GPU
+
+# BASELINE configs: C3 512^3 (M=1); C4 per-GPU slab (128,4,1024,1024) with reg_time=2^-5; C5 per-GPU slab (64,8,2048,2048)
+C3 = ((512, 1, 512, 512), dict())
+C4 = ((128, 4, 1024, 1024), dict(reg_time=2 ** -5))
+C5 = ((64, 8, 2048, 2048), dict(reg_time=2 ** -5))
+
+
+def _free():
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+
+
+def _dot64(a, b):
+    """<a, b> accumulated in float64, one leading-axis slice at a time (no field-sized temporaries)."""
+    tot = 0.0
+    for k in range(a.shape[0]):
+        tot += float((a[k].double() * b[k].double()).sum())
+    return tot
+
+
+@pytest.mark.parametrize("shape,kw", [C3, C4], ids=["C3_512cube", "C4_slab"])
+def test_hybrid_adjointness_and_tv_identity(shape, kw):
+    torch.manual_seed(0)
+    x = torch.rand(shape, device="cuda")
+    Dx = opG.D_hybrid(x, **kw)
+    tv, G = tvG.tv_hybrid(x, return_pytorch_tensor=True, **kw)
+    l21 = opG.compute_L21_norm(Dx)
+    assert float(tv) == pytest.approx(float(l21), rel=1e-6)           # fused TV == L21(D x) by separate kernels
+    # <D x, p> = <x, D^T p> with p = D x (so the check needs no second field-sized random array)
+    a = _dot64(Dx, Dx)
+    DTDx = opG.D_T_hybrid(Dx, **kw)
+    b = _dot64(x, DTDx)
+    assert abs(a - b) / abs(a) < 1e-5
+    # scale laws: TV(c x) = c TV(x), G(c x) = G(x) up to rounding; TV(x + const) = TV(x)
+    tv2, G2 = tvG.tv_hybrid(2.0 * x, return_pytorch_tensor=True, **kw)
+    assert float(tv2) == pytest.approx(2 * float(tv), rel=1e-6)
+    assert max(float((G2[k] - G[k]).abs().max()) for k in range(G.shape[0])) < 1e-5
+    del Dx, DTDx, G, G2
+    _free()
+
+
+def test_constant_volume_has_zero_tv_and_gradient():
+    shape, kw = C4
+    x = torch.full(shape, 3.25, device="cuda")
+    for name in ("upwind", "downwind", "central", "hybrid"):
+        tv, G, n = getattr(tvG, "tv_" + name)(x, return_pytorch_tensor=True, return_grad_norms=True, **kw)
+        assert float(tv) == 0.0
+        assert not bool(G.any())
+        assert bool(torch.isinf(n).all())
+        del G, n
+    _free()
+
+
+@pytest.mark.parametrize("scheme", ["upwind", "downwind", "central", "hybrid"])
+def test_schemes_with_mask_on_C5_slab(scheme):
+    """BASELINE config 5 (one GPU's slab): disc mask, static disc with factor 4, reg_time = 2^-5."""
+    shape, kw = C5
+    Nz, M, N, _ = shape
+    torch.manual_seed(1)
+    x = torch.rand(shape, device="cuda")
+    ii, jj = torch.meshgrid(torch.arange(N, device="cuda"), torch.arange(N, device="cuda"), indexing="ij")
+    r2 = (ii - N / 2 + 0.5) ** 2 + (jj - N / 2 + 0.5) ** 2
+    mask = (r2 < (0.48 * N) ** 2)
+    ms = (r2 < (0.25 * N) ** 2).reshape(1, 1, N, N)
+    kw = dict(kw, mask_static=ms, factor_reg_static=4.0)
+    tv, G = getattr(tvG, "tv_" + scheme)(x, mask=mask, return_pytorch_tensor=True, **kw)
+    assert all(not bool(x[k][:, ~mask].any()) for k in range(Nz))     # zeroed in place
+    # far outside the disc the image is zero: no TV contribution, zero sub-gradient
+    assert not bool(G[:, :, :8, :8].any())
+    del G
+    _free()
+    Dx = getattr(opG, "D_" + scheme)(x, **kw)
+    assert float(tv) == pytest.approx(float(opG.compute_L21_norm(Dx)), rel=1e-6)
+    a = _dot64(Dx, Dx)
+    DTDx = getattr(opG, "D_T_" + scheme)(Dx, **kw)
+    b = _dot64(x, DTDx)
+    assert abs(a - b) / abs(a) < 1e-5
+    del Dx, DTDx
+    _free()
+
+
+def test_cp_iteration_on_C4_slab_equals_two_half_slabs():
+    """A whole-volume hybrid CP iteration is bitwise equal to the same iteration computed as two z-slabs with
+    halo planes: the multi-GPU decomposition, exercised at full size on one GPU."""
+    shape, kw = C4
+    Nz, M, N, _ = shape
+    lib = _lib.lib()
+    torch.manual_seed(2)
+    x0 = torch.rand(shape, device="cuda") + 0.05 * torch.randn(shape, device="cuda")
+    s = pytv.CPSolver(x0, lam=0.1, scheme="hybrid", variant="rof", **kw)
+    s.step(2)                                 # a non-trivial state (x, xbar, y)
+    xbar, x, y = s.aux.clone(), s.x.clone(), s.y.clone()
+    s.step(1)
+    e_whole = s.energy()
+    st = _dev.stream_ptr()
+    half = Nz // 2
+    scal = torch.zeros(4, dtype=torch.float64, device="cuda")
+    # pass A on both slabs (y updated in place, slab views are contiguous in a z-major layout)
+    for k, (a, b) in enumerate(((0, half), (half, Nz))):
+        pb = _lib.make_problem("hybrid", _lib.F32, (b - a, M, N, N), 1.0, kw["reg_time"], 0.0, None, a, Nz)
+        lo = xbar[a - 1] if a > 0 else None
+        hi = xbar[b] if b < Nz else None
+        _lib.check(lib.pytvb_cp_dual(ctypes.byref(pb), _dev.ptr(xbar[a:b]), _dev.ptr(y[a:b]), 0.1, s.sigma, _dev.ptr(scal[k:k + 1]), _dev.ptr(lo),
+                                     _dev.ptr(hi), _dev.ptr(s.ws), st))
+    ylo, yhi = y[half - 1, 4].clone(), y[half, 5].clone()
+    for k, (a, b) in enumerate(((0, half), (half, Nz))):
+        pb = _lib.make_problem("hybrid", _lib.F32, (b - a, M, N, N), 1.0, kw["reg_time"], 0.0, None, a, Nz)
+        _lib.check(lib.pytvb_cp_primal_rof(ctypes.byref(pb), _dev.ptr(y[a:b]), _dev.ptr(x[a:b]), _dev.ptr(xbar[a:b]), _dev.ptr(s.x0[a:b]), s.tau,
+                                           s.theta, _dev.ptr(scal[2 + k:3 + k]), _dev.ptr(ylo if a > 0 else None), _dev.ptr(yhi if b < Nz else None),
+                                           _dev.ptr(s.ws), st))
+    assert torch.equal(y, s.y) and torch.equal(x, s.x) and torch.equal(xbar, s.aux)
+    l21, fid = float(scal[0] + scal[1]), float(scal[2] + scal[3])
+    assert 0.5 * fid + 0.1 * l21 == pytest.approx(e_whole, rel=1e-12)
+    del s, x, y, xbar
+    _free()

