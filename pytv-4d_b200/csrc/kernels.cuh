@@ -18,6 +18,32 @@ namespace pytvb {
 constexpr int CTA_THREADS = 256;
 constexpr int BAND_ROWS = 64;
 
+// Division by a runtime constant as multiply-high + shift (valid for 0 <= n < 2^31): the block-index decode
+// below would otherwise spend ~30 instructions per integer division.
+struct FastDiv {
+    unsigned d, mul, shr;
+    __host__ __device__ __forceinline__ void divmod(unsigned n, unsigned& q, unsigned& r) const {
+#if defined(__CUDA_ARCH__)
+        q = (d != 1) ? (__umulhi(n, mul) >> shr) : n;
+#else
+        q = (d != 1) ? (unsigned)(((unsigned long long)n * mul) >> 32) >> shr : n;
+#endif
+        r = n - q * d;
+    }
+};
+inline FastDiv make_fastdiv(unsigned d) {
+    FastDiv f;
+    f.d = d; f.mul = 0; f.shr = 0;
+    if (d > 1) {
+        unsigned lg = 0;
+        while ((1ull << lg) < d) ++lg;              // ceil(log2 d)
+        const unsigned p = 31 + lg;
+        f.mul = (unsigned)(((1ull << p) + d - 1) / d);
+        f.shr = p - 32;
+    }
+    return f;
+}
+
 // Thread -> quad mapping.
 struct Tiling {
     int W;          // quads per row
@@ -28,6 +54,8 @@ struct Tiling {
     int z_lo, nz;   // z range covered: z_lo .. z_lo+nz-1 (z_lo = -1 when a halo plane is processed too)
     int M;
     long long nblocks;
+    FastDiv d_ncb, d_RB, d_M, d_nz;
+    int tw_shift;   // TW == 1 << tw_shift
 };
 
 inline Tiling make_tiling(int Nj, int Ni, int M, int z_lo, int nz, int vec) {
@@ -48,6 +76,12 @@ inline Tiling make_tiling(int Nj, int Ni, int M, int z_lo, int nz, int vec) {
     t.nz = nz;
     t.M = M;
     t.nblocks = (long long)t.ncb * t.RB * M * nz * t.nbands;
+    t.d_ncb = make_fastdiv((unsigned)t.ncb);
+    t.d_RB = make_fastdiv((unsigned)t.RB);
+    t.d_M = make_fastdiv((unsigned)M);
+    t.d_nz = make_fastdiv((unsigned)nz);
+    t.tw_shift = 0;
+    while ((1 << t.tw_shift) < t.TW) ++t.tw_shift;
     return t;
 }
 
@@ -58,15 +92,17 @@ struct QuadIdx {
 
 __device__ __forceinline__ QuadIdx decode_quad(const Tiling& tl, int Ni, int vec) {
     QuadIdx q;
-    const int tq = threadIdx.x % tl.TW, tr = threadIdx.x / tl.TW;
-    long long b = blockIdx.x;
-    const int cb = (int)(b % tl.ncb); b /= tl.ncb;
-    const int rbi = (int)(b % tl.RB); b /= tl.RB;
-    q.t = (int)(b % tl.M); b /= tl.M;
-    q.z = tl.z_lo + (int)(b % tl.nz); b /= tl.nz;
+    const int tq = threadIdx.x & (tl.TW - 1), tr = threadIdx.x >> tl.tw_shift;
+    unsigned b = blockIdx.x, cb, rbi, t, zi;
+    tl.d_ncb.divmod(b, b, cb);
+    tl.d_RB.divmod(b, b, rbi);
+    tl.d_M.divmod(b, b, t);
+    tl.d_nz.divmod(b, b, zi);
+    q.t = (int)t;
+    q.z = tl.z_lo + (int)zi;
     const int band = (int)b;
-    q.i = (band * tl.RB + rbi) * tl.TR + tr;
-    const int qi = cb * tl.TW + tq;
+    q.i = (band * tl.RB + (int)rbi) * tl.TR + tr;
+    const int qi = (int)cb * tl.TW + tq;
     q.j0 = qi * vec;
     q.active = (q.i < Ni) && (qi < tl.W);
     return q;

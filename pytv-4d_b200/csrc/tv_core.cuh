@@ -170,9 +170,15 @@ PYTVB_HD T axis_diff(T c, T minus, T plus, bool v_m, bool v_p, bool fallback) {
     return (v_m && v_p) ? plus - minus : T(0);
 }
 
-// D_scheme at a quad: d[comp][e], identical to the reference's operator output (weights, mask_static and
-// the global divisor applied; division, not reciprocal multiply, to stay closest to `D_img/np.sqrt(2.0)`).
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON>
+// Global divisor of a scheme.  EXACT: a true division, to stay closest to the reference's
+// `D_img/np.sqrt(2.0)` (operator kernels); otherwise a multiply by the reciprocal (fused kernels, where
+// eight IEEE divisions per voxel would be a third of the instruction stream).
+template <typename T, bool EXACT>
+PYTVB_HD T apply_div(T v, const Params<T>& P) { return EXACT ? v / P.div : v * P.inv_div; }
+
+// D_scheme at a quad: d[comp][e], the reference's operator output (weights, mask_static and the global
+// divisor applied).
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, bool EXACT = true>
 PYTVB_HD void diffs_from_nbhd(T (*d)[VEC], const Nbhd<T, VEC>& n, const Params<T>& P, int i, int j0) {
     typedef Comp<SCHEME, Z_ON, T_ON> C;
     T fac[VEC];
@@ -183,34 +189,34 @@ PYTVB_HD void diffs_from_nbhd(T (*d)[VEC], const Nbhd<T, VEC>& n, const Params<T
         const T c = n.c[e + 1];
         const bool v_l = j > 0, v_r = j < P.Nj - 1;
         if (SCHEME == HYBRID) {
-            d[C::I_F][e] = (n.v_dn ? n.dn[e] - c : T(0)) / P.div;
-            d[C::J_F][e] = (v_r ? n.c[e + 2] - c : T(0)) / P.div;
-            d[C::I_B][e] = (n.v_up ? c - n.up[e] : T(0)) / P.div;
-            d[C::J_B][e] = (v_l ? c - n.c[e] : T(0)) / P.div;
+            d[C::I_F][e] = apply_div<T, EXACT>((n.v_dn ? n.dn[e] - c : T(0)), P);
+            d[C::J_F][e] = apply_div<T, EXACT>((v_r ? n.c[e + 2] - c : T(0)), P);
+            d[C::I_B][e] = apply_div<T, EXACT>((n.v_up ? c - n.up[e] : T(0)), P);
+            d[C::J_B][e] = apply_div<T, EXACT>((v_l ? c - n.c[e] : T(0)), P);
             if (Z_ON) {
-                d[C::Z_F][e] = (n.v_zp ? P.srz * (n.zp[e] - c) : T(0)) / P.div;
-                d[C::Z_B][e] = (n.v_zm ? P.srz * (c - n.zm[e]) : T(0)) / P.div;
+                d[C::Z_F][e] = apply_div<T, EXACT>((n.v_zp ? P.srz * (n.zp[e] - c) : T(0)), P);
+                d[C::Z_B][e] = apply_div<T, EXACT>((n.v_zm ? P.srz * (c - n.zm[e]) : T(0)), P);
             }
             if (T_ON) {
-                d[C::T_F][e] = (n.v_tp ? P.srt * (n.tp[e] - c) * fac[e] : T(0)) / P.div;
-                d[C::T_B][e] = (n.v_tm ? P.srt * (c - n.tm[e]) * fac[e] : T(0)) / P.div;
+                d[C::T_F][e] = apply_div<T, EXACT>((n.v_tp ? P.srt * (n.tp[e] - c) * fac[e] : T(0)), P);
+                d[C::T_B][e] = apply_div<T, EXACT>((n.v_tm ? P.srt * (c - n.tm[e]) * fac[e] : T(0)), P);
             }
         } else {
-            d[C::I_F][e] = axis_diff<T, SCHEME>(c, n.up[e], n.dn[e], n.v_up, n.v_dn, false) / P.div;
-            d[C::J_F][e] = axis_diff<T, SCHEME>(c, n.c[e], n.c[e + 2], v_l, v_r, false) / P.div;
+            d[C::I_F][e] = apply_div<T, EXACT>(axis_diff<T, SCHEME>(c, n.up[e], n.dn[e], n.v_up, n.v_dn, false), P);
+            d[C::J_F][e] = apply_div<T, EXACT>(axis_diff<T, SCHEME>(c, n.c[e], n.c[e + 2], v_l, v_r, false), P);
             if (Z_ON)
-                d[C::Z_F][e] = P.srz * axis_diff<T, SCHEME>(c, n.zm[e], n.zp[e], n.v_zm, n.v_zp, P.z_fwd_fallback != 0) / P.div;
+                d[C::Z_F][e] = apply_div<T, EXACT>(P.srz * axis_diff<T, SCHEME>(c, n.zm[e], n.zp[e], n.v_zm, n.v_zp, P.z_fwd_fallback != 0), P);
             if (T_ON)
-                d[C::T_F][e] = P.srt * axis_diff<T, SCHEME>(c, n.tm[e], n.tp[e], n.v_tm, n.v_tp, P.t_fwd_fallback != 0) * fac[e] / P.div;
+                d[C::T_F][e] = apply_div<T, EXACT>(P.srt * axis_diff<T, SCHEME>(c, n.tm[e], n.tp[e], n.v_tm, n.v_tp, P.t_fwd_fallback != 0) * fac[e], P);
         }
     }
 }
 
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON>
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, bool EXACT = true>
 PYTVB_HD void quad_D(T (*d)[VEC], const ImgView<T>& X, const Params<T>& P, int z, int t, int i, int j0) {
     Nbhd<T, VEC> n;
     load_nbhd<T, VEC, SCHEME, Z_ON, T_ON>(n, X, P, z, t, i, j0);
-    diffs_from_nbhd<T, VEC, SCHEME, Z_ON, T_ON>(d, n, P, i, j0);
+    diffs_from_nbhd<T, VEC, SCHEME, Z_ON, T_ON, EXACT>(d, n, P, i, j0);
 }
 
 // 2-norm over the components at each voxel of the quad.
@@ -284,7 +290,7 @@ PYTVB_HD void adj_axis_rows(T* acc, T w, long long k, long long L, bool fallback
 }
 
 // D_T_scheme at a quad: out[e] (weights, mask_static on the time part, global divisor).
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON>
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, bool EXACT = true>
 PYTVB_HD void quad_DT(T* out, const FieldView<T>& Pf, const Params<T>& P, int z, int t, int i, int j0) {
     typedef Comp<SCHEME, Z_ON, T_ON> C;
     T acc[VEC];
@@ -332,7 +338,7 @@ PYTVB_HD void quad_DT(T* out, const FieldView<T>& Pf, const Params<T>& P, int z,
         for (int e = 0; e < VEC; ++e) acc[e] += tacc[e] * fac[e];
     }
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) out[e] = acc[e] / P.div;
+    for (int e = 0; e < VEC; ++e) out[e] = apply_div<T, EXACT>(acc[e], P);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -446,7 +452,7 @@ PYTVB_HD T quad_cp_dual(T* y, const ImgView<T>& Xb, const Params<T>& P, T sigma,
     T* yq = y + (long long)z * P.sZf + (long long)t * P.sT + (long long)i * P.Nj + j0;
 #pragma unroll
     for (int k = 0; k < ND; ++k) ld_into<T, VEC>(yn[k], yq + (long long)k * P.sC);
-    quad_D<T, VEC, SCHEME, Z_ON, T_ON>(d, Xb, P, z, t, i, j0);
+    quad_D<T, VEC, SCHEME, Z_ON, T_ON, false>(d, Xb, P, z, t, i, j0);
     T l21 = T(0);
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
@@ -479,7 +485,7 @@ template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON>
 PYTVB_HD T quad_cp_primal_rof(T* x, T* xbar, const T* x0, const FieldView<T>& Y, const Params<T>& P, T tau, T theta,
                               int z, int t, int i, int j0) {
     T dty[VEC];
-    quad_DT<T, VEC, SCHEME, Z_ON, T_ON>(dty, Y, P, z, t, i, j0);
+    quad_DT<T, VEC, SCHEME, Z_ON, T_ON, false>(dty, Y, P, z, t, i, j0);
     const long long off = (long long)z * P.sZ + (long long)t * P.sT + (long long)i * P.Nj + j0;
     const Pack<T, VEC> xo = ld_pack<T, VEC>(x + off), x0q = ld_pack<T, VEC>(x0 + off);
     Pack<T, VEC> xn, xb;
@@ -503,7 +509,7 @@ template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON>
 PYTVB_HD T quad_cp_primal_readme(T* x, T* y_f, const T* x0, const FieldView<T>& Y, const Params<T>& P, T tau, T sigma_A,
                                  int z, int t, int i, int j0) {
     T dty[VEC];
-    quad_DT<T, VEC, SCHEME, Z_ON, T_ON>(dty, Y, P, z, t, i, j0);
+    quad_DT<T, VEC, SCHEME, Z_ON, T_ON, false>(dty, Y, P, z, t, i, j0);
     const long long off = (long long)z * P.sZ + (long long)t * P.sT + (long long)i * P.Nj + j0;
     const Pack<T, VEC> xo = ld_pack<T, VEC>(x + off), x0q = ld_pack<T, VEC>(x0 + off), yfo = ld_pack<T, VEC>(y_f + off);
     Pack<T, VEC> xn, yfn;
