@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libpytv_b200.so")
+LIB_PATH = os.environ.get("PYTVB_LIB_PATH") or os.path.join(_HERE, "csrc", "libpytv_b200.so")   # override: tuning builds
 
 SCHEME_ID = {"upwind": 0, "downwind": 1, "central": 2, "hybrid": 3}
 F32, F64 = 0, 1

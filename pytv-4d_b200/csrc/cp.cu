@@ -1,13 +1,40 @@
 // Fused Chambolle-Pock iteration: dual pass (A) and primal pass (B).
+#include <stdlib.h>
+
 #include "host_common.cuh"
+#include "kernels2.cuh"
+
+#ifndef PYTVB_STRIP_R
+#define PYTVB_STRIP_R 4   // image rows walked by one thread in the generation-2 kernels
+#endif
 
 using namespace pytvb;
 
 namespace {
 
-template <typename T> struct DualArgs { ImgView<T> Xb; T* y; double* partial; Params<T> P; T sigma, inv_lam; cudaStream_t st; long long* nb; };
+// Generation 2 (strip kernels) serves every vectorised call; generation 1 remains for the scalar path
+// (row length not divisible by the vector width, unaligned pointers) and can be forced with PYTVB_GEN=1.
+bool use_gen2() {
+    const char* e = getenv("PYTVB_GEN");
+    return !e || atoi(e) >= 2;
+}
+
+template <typename T> struct DualArgs { ImgView<T> Xb; T* y; double* partial; Params<T> P; T sigma, inv_lam, lam; cudaStream_t st; long long* nb; };
 template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchDual {
     static int run(const DualArgs<T>& a) {
+        if constexpr (VEC > 1) {
+            if (use_gen2()) {
+                constexpr int R = PYTVB_STRIP_R;
+                const Tiling tl = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.P.Nz, VEC);
+                if (int rc = check_grid(tl)) return rc;
+                cp_dual_strip_kernel<T, VEC, SCHEME, Z, TT, R><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(
+                    a.Xb, a.y, a.partial, a.P, a.sigma * a.P.inv_div, a.lam, tl);
+                count_launches(1);
+                PYTVB_CUDA(cudaGetLastError());
+                *a.nb = tl.nblocks;
+                return PYTVB_OK;
+            }
+        }
         const Tiling tl = make_tiling(a.P.Nj, a.P.Ni, a.P.M, 0, a.P.Nz, VEC);
         if (int rc = check_grid(tl)) return rc;
         cp_dual_kernel<T, VEC, SCHEME, Z, TT><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.Xb, a.y, a.partial, a.P, a.sigma, a.inv_lam, tl);
@@ -23,6 +50,24 @@ template <typename T> struct PrimalArgs {
 };
 template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchPrimal {
     static int run(const PrimalArgs<T>& a) {
+        if constexpr (VEC > 1) {
+            if (use_gen2()) {
+                constexpr int R = PYTVB_STRIP_R;
+                const Tiling tl = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.P.Nz, VEC);
+                if (int rc = check_grid(tl)) return rc;
+                const T c1 = T(1) / (T(1) + (a.variant == 0 ? a.tau : a.c2));
+                if (a.variant == 0)
+                    cp_primal_strip_kernel<T, VEC, SCHEME, Z, TT, 0, R><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(
+                        a.Y, a.x, a.aux, a.x0, a.partial, a.P, a.tau, c1, a.c2, tl);
+                else
+                    cp_primal_strip_kernel<T, VEC, SCHEME, Z, TT, 1, R><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(
+                        a.Y, a.x, a.aux, a.x0, a.partial, a.P, a.tau, c1, a.c2, tl);
+                count_launches(1);
+                PYTVB_CUDA(cudaGetLastError());
+                *a.nb = tl.nblocks;
+                return PYTVB_OK;
+            }
+        }
         const Tiling tl = make_tiling(a.P.Nj, a.P.Ni, a.P.M, 0, a.P.Nz, VEC);
         if (int rc = check_grid(tl)) return rc;
         if (a.variant == 0)
@@ -47,6 +92,7 @@ int run_dual(const pytvb_problem* pb, const void* xbar, void* y, double lam, dou
     a.P = make_params<T>(pb);
     a.sigma = (T)sigma;
     a.inv_lam = (T)(1.0 / lam);
+    a.lam = (T)lam;
     a.st = st;
     long long nb = 0;
     a.nb = &nb;

@@ -1,0 +1,334 @@
+// Generation-2 per-thread code of the two Chambolle-Pock passes: instruction-lean "strip" form.
+//
+// Why: generation 1 (tv_core.cuh, one quad per thread) moved exactly the algorithmic bytes but spent ~1300
+// instructions per quad (IEEE divisions, 64-bit block decode, a 64-bit address computation and a boundary
+// predicate per neighbour load) and ran at 62 % (pass A) / 82 % (pass B) of the measured HBM peak with the
+// issue slots 50-60 % busy (profiles/r01a_gen1_cp_ncu_full.txt).  Here:
+//   * everything that depends only on (z, t) - plane base pointers of the centre and of the z / t
+//     neighbours, weights, boundary factors - is computed once per CTA and is warp-uniform;
+//   * a thread walks R consecutive rows of one quad column and addresses every array as
+//     `uniform plane pointer + 32-bit element offset`;
+//   * neighbours that do not exist are CLAMPED to the centre, which makes the difference exactly zero
+//     (x[k] - x[k] = 0: the reference's "out-of-range difference is zero" rule, tv_operators_CPU.py:118)
+//     without a predicate; only the centred scheme needs 0/1 factors;
+//   * the projection uses one rsqrt: scale = min(1, lam * rsqrt(|y|^2)); no division.
+// The functions are __host__ __device__ (plain loads only) so tests/emul runs them on the CPU too.
+#pragma once
+#include "tv_core.cuh"
+
+namespace pytvb {
+
+PYTVB_HD float fast_rsqrt(float a) {
+#if defined(__CUDA_ARCH__)
+    return rsqrtf(a);            // MUFU.RSQ + one fix-up, ~2 ulp
+#else
+    return 1.0f / sqrtf(a);
+#endif
+}
+PYTVB_HD double fast_rsqrt(double a) { return 1.0 / sqrt(a); }
+PYTVB_HD float fast_sqrt(float a) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(a));   // MUFU.SQRT, no IEEE slow path (feeds a sum of 1e8+ terms)
+    return r;
+#else
+    return sqrtf(a);
+#endif
+}
+PYTVB_HD double fast_sqrt(double a) { return sqrt(a); }
+
+// Warp-uniform context of one (z, t) image plane for the dual pass.
+template <typename T>
+struct DualPlane {
+    const T* c;                       // plane (z, t) of xbar
+    const T* zm; const T* zp;         // planes (z-1, t), (z+1, t): clamped to c at the volume boundary, halo planes at slab edges
+    const T* tm; const T* tp;         // planes (z, t-1), (z, t+1), clamped
+    T* y;                             // component 0 of y at plane (z, t); component k at + k*sC
+    T fz, ft;                         // centred scheme only: 1 where the centred z / t difference exists, else 0
+};
+
+template <typename T, int SCHEME>
+PYTVB_HD DualPlane<T> make_dual_plane(const ImgView<T>& X, T* y, const Params<T>& P, int z, int t) {
+    DualPlane<T> d;
+    const long long zg = P.zg0 + z;
+    const bool v_zm = zg > 0, v_zp = zg < P.NzG - 1, v_tm = t > 0, v_tp = t < P.M - 1;
+    d.c = X.row(P, z, t, 0);
+    d.zm = v_zm ? X.row(P, z - 1, t, 0) : d.c;
+    d.zp = v_zp ? X.row(P, z + 1, t, 0) : d.c;
+    d.tm = v_tm ? X.row(P, z, t - 1, 0) : d.c;
+    d.tp = v_tp ? X.row(P, z, t + 1, 0) : d.c;
+    d.y = y + (long long)z * P.sZf + (long long)t * P.sT;
+    d.fz = d.ft = T(1);
+    if (SCHEME == CENTRAL) {
+        // centred difference exists iff both neighbours do; on a length-2 axis it degrades to the forward
+        // difference (minus pointer := centre, the clamped plus pointer already gives 0 on the last plane)
+        if (P.z_fwd_fallback) d.zm = d.c; else d.fz = (v_zm && v_zp) ? T(1) : T(0);
+        if (P.t_fwd_fallback) d.tm = d.c; else d.ft = (v_tm && v_tp) ? T(1) : T(0);
+    }
+    return d;
+}
+
+// One quad of the dual pass.  o = i*Nj + j0; o_up / o_dn = offsets of rows i-1 / i+1 clamped to [0, Ni).
+// sig = sigma * inv_div (so that y + sigma*D = y + sig*raw_difference).  Returns sum_e sqrt(sum_k raw_k^2)
+// (the caller multiplies the total by inv_div to get L21(D xbar)).
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON>
+PYTVB_HD T strip_quad_cp_dual(const DualPlane<T>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn, T sig, T lam) {
+    typedef Comp<SCHEME, Z_ON, T_ON> C;
+    constexpr int ND = C::ND;
+    T c[VEC + 2], up[VEC], dn[VEC], zm[VEC], zp[VEC], tm[VEC], tp[VEC], y[ND][VEC], d[ND][VEC];
+#pragma unroll
+    for (int k = 0; k < ND; ++k) ld_into<T, VEC>(y[k], pl.y + (long long)k * P.sC + o);
+    ld_into<T, VEC>(c + 1, pl.c + o);
+    c[0] = (C::NEED_BWD && j0 > 0) ? pl.c[o - 1] : c[1];
+    c[VEC + 1] = (C::NEED_FWD && j0 + VEC < P.Nj) ? pl.c[o + VEC] : c[VEC];
+    if (C::NEED_BWD) ld_into<T, VEC>(up, pl.c + o_up);
+    if (C::NEED_FWD) ld_into<T, VEC>(dn, pl.c + o_dn);
+    if (Z_ON && C::NEED_BWD) ld_into<T, VEC>(zm, pl.zm + o);
+    if (Z_ON && C::NEED_FWD) ld_into<T, VEC>(zp, pl.zp + o);
+    if (T_ON && C::NEED_BWD) ld_into<T, VEC>(tm, pl.tm + o);
+    if (T_ON && C::NEED_FWD) ld_into<T, VEC>(tp, pl.tp + o);
+    T fac[VEC];
+    if (T_ON) static_factor<T, VEC>(fac, P, i, j0);
+    // centred scheme: in-plane factors (rows: uniform per row; columns: only the volume's first / last column)
+    const T fi = (SCHEME == CENTRAL) ? ((i > 0 && i < P.Ni - 1) ? T(1) : T(0)) : T(1);
+    T l21 = T(0);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        const T x = c[e + 1];
+        if (SCHEME == HYBRID) {
+            d[C::I_F][e] = dn[e] - x;
+            d[C::J_F][e] = c[e + 2] - x;
+            d[C::I_B][e] = x - up[e];
+            d[C::J_B][e] = x - c[e];
+            if (Z_ON) { d[C::Z_F][e] = P.srz * (zp[e] - x); d[C::Z_B][e] = P.srz * (x - zm[e]); }
+            if (T_ON) { const T w = P.srt * fac[e]; d[C::T_F][e] = w * (tp[e] - x); d[C::T_B][e] = w * (x - tm[e]); }
+        } else if (SCHEME == UPWIND) {
+            d[0][e] = dn[e] - x;
+            d[1][e] = c[e + 2] - x;
+            if (Z_ON) d[C::Z_F][e] = P.srz * (zp[e] - x);
+            if (T_ON) d[C::T_F][e] = P.srt * fac[e] * (tp[e] - x);
+        } else if (SCHEME == DOWNWIND) {
+            d[0][e] = x - up[e];
+            d[1][e] = x - c[e];
+            if (Z_ON) d[C::Z_F][e] = P.srz * (x - zm[e]);
+            if (T_ON) d[C::T_F][e] = P.srt * fac[e] * (x - tm[e]);
+        } else {
+            const int j = j0 + e;
+            const T fj = (j > 0 && j < P.Nj - 1) ? T(1) : T(0);
+            d[0][e] = fi * (dn[e] - up[e]);
+            d[1][e] = fj * (c[e + 2] - c[e]);
+            if (Z_ON) d[C::Z_F][e] = (P.srz * pl.fz) * (zp[e] - zm[e]);
+            if (T_ON) d[C::T_F][e] = (P.srt * pl.ft * fac[e]) * (tp[e] - tm[e]);
+        }
+        T s = T(0), sd = T(0);
+#pragma unroll
+        for (int k = 0; k < ND; ++k) {
+            sd += d[k][e] * d[k][e];
+            y[k][e] += sig * d[k][e];
+            s += y[k][e] * y[k][e];
+        }
+        l21 += fast_sqrt(sd);
+        // y / max(1, |y|/lam)  ==  y * min(1, lam / |y|);  |y| = 0 gives rsqrt = inf -> min = 1
+        const T r = lam * fast_rsqrt(s);
+        const T scale = r < T(1) ? r : T(1);   // a NaN (lam = 0 and y = 0) falls through to 1
+#pragma unroll
+        for (int k = 0; k < ND; ++k) y[k][e] *= scale;
+    }
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+        Pack<T, VEC> pk;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) pk.v[e] = y[k][e];
+        st_pack<T, VEC>(pl.y + (long long)k * P.sC + o, pk);
+    }
+    return l21;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-uniform context of one (z, t) plane for the primal pass.
+template <typename T>
+struct PrimalPlane {
+    const T* y;        // component 0 of y at plane (z, t)
+    const T* zf_m;     // forward-type z component at plane z-1 (halo at a slab edge); any valid pointer when unused
+    const T* zb_p;     // backward-type z component at plane z+1
+    const T* tf_m;     // forward-type t component at plane t-1
+    const T* tb_p;     // backward-type t component at plane t+1
+    T az, bz, at, bt;  // weights * existence factors of the minus / plus z and t terms (see adjoint rule below)
+    long long img;     // offset of image plane (z, t) in x / xbar / x0
+};
+
+// Adjoint rule per axis (tv_operators_CPU.py:555-560, :488-493, :623-628), k = index along the axis:
+//   forward-type slot F:  + [k>0] F[k-1] - [k<L-1] F[k]          backward-type slot B:  + [k>0] B[k] - [k<L-1] B[k+1]
+//   centred slot C:       + [k>=2] C[k-1] - [k<=L-3] C[k+1]      (length-2 z / t axis: the forward rule)
+template <typename T, int SCHEME>
+PYTVB_HD void adj_factors(T& a, T& b, long long k, long long L, bool fallback) {
+    if (SCHEME == CENTRAL && !fallback) {
+        a = (k >= 2) ? T(1) : T(0);
+        b = (k <= L - 3) ? T(1) : T(0);
+    } else {
+        a = (k > 0) ? T(1) : T(0);
+        b = (k < L - 1) ? T(1) : T(0);
+    }
+}
+
+template <typename T, int SCHEME, bool Z_ON, bool T_ON>
+PYTVB_HD PrimalPlane<T> make_primal_plane(const FieldView<T>& Y, const Params<T>& P, int z, int t) {
+    typedef Comp<SCHEME, Z_ON, T_ON> C;
+    PrimalPlane<T> p;
+    p.y = Y.row(P, z, 0, t, 0);
+    p.img = (long long)z * P.sZ + (long long)t * P.sT;
+    p.zf_m = p.zb_p = p.tf_m = p.tb_p = p.y;
+    p.az = p.bz = p.at = p.bt = T(0);
+    if (Z_ON) {
+        const long long zg = P.zg0 + z;
+        T a, b;
+        adj_factors<T, SCHEME>(a, b, zg, P.NzG, P.z_fwd_fallback != 0);
+        p.az = a * P.srz;
+        p.bz = b * P.srz;
+        if (zg > 0) p.zf_m = Y.row(P, z - 1, C::Z_F, t, 0);
+        if (zg < P.NzG - 1) p.zb_p = Y.row(P, z + 1, C::Z_B, t, 0);
+    }
+    if (T_ON) {
+        T a, b;
+        adj_factors<T, SCHEME>(a, b, t, P.M, P.t_fwd_fallback != 0);
+        p.at = a * P.srt;
+        p.bt = b * P.srt;
+        if (t > 0) p.tf_m = Y.row(P, z, C::T_F, t - 1, 0);
+        if (t < P.M - 1) p.tb_p = Y.row(P, z, C::T_B, t + 1, 0);
+    }
+    return p;
+}
+
+// minus-side and plus-side operands of one axis given the slot values at k-1 / k / k+1:
+//   upwind: (F[k-1], F[k])   downwind: (B[k], B[k+1])   hybrid: (F[k-1]+B[k], F[k]+B[k+1])   central: (C[k-1], C[k+1])
+template <typename T, int SCHEME>
+PYTVB_HD void adj_operands(T& m, T& p, T f_m, T f_c, T b_c, T b_p, bool fallback) {
+    if (SCHEME == UPWIND || (SCHEME == CENTRAL && fallback)) { m = f_m; p = f_c; }
+    else if (SCHEME == DOWNWIND) { m = b_c; p = b_p; }
+    else if (SCHEME == HYBRID) { m = f_m + b_c; p = f_c + b_p; }
+    else { m = f_m; p = b_p; }
+}
+
+// D^T y at one quad (times inv_div), strip addressing.
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON>
+PYTVB_HD void strip_quad_DT(T* out, const PrimalPlane<T>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn) {
+    typedef Comp<SCHEME, Z_ON, T_ON> C;
+    constexpr bool NF = (SCHEME != DOWNWIND);   // reads the forward-type slot at k-1 (centred: C[k-1])
+    constexpr bool NB = (SCHEME != UPWIND);     // reads the backward-type slot at k+1 (centred: C[k+1])
+    constexpr bool CTR = (SCHEME == CENTRAL);
+    const T* yI_F = pl.y + (long long)C::I_F * P.sC;
+    const T* yI_B = pl.y + (long long)C::I_B * P.sC;
+    const T* yJ_F = pl.y + (long long)C::J_F * P.sC;
+    const T* yJ_B = pl.y + (long long)C::J_B * P.sC;
+    T acc[VEC];
+    // ---- rows
+    {
+        T a, b, f_m[VEC], f_c[VEC], b_c[VEC], b_p[VEC];
+        adj_factors<T, SCHEME>(a, b, i, P.Ni, false);
+        if (NF) ld_into<T, VEC>(f_m, yI_F + o_up); else zero_into<T, VEC>(f_m);
+        if (!CTR && NF) ld_into<T, VEC>(f_c, yI_F + o); else zero_into<T, VEC>(f_c);
+        if (!CTR && NB) ld_into<T, VEC>(b_c, yI_B + o); else zero_into<T, VEC>(b_c);
+        if (NB) ld_into<T, VEC>(b_p, yI_B + o_dn); else zero_into<T, VEC>(b_p);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            T m, p;
+            adj_operands<T, SCHEME>(m, p, f_m[e], f_c[e], b_c[e], b_p[e], false);
+            acc[e] = a * m - b * p;
+        }
+    }
+    // ---- columns
+    {
+        T f[VEC + 2], bq[VEC + 2];
+#pragma unroll
+        for (int e = 0; e < VEC + 2; ++e) bq[e] = T(0);
+        ld_into<T, VEC>(f + 1, yJ_F + o);
+        f[0] = (NF && j0 > 0) ? yJ_F[o - 1] : T(0);
+        f[VEC + 1] = (CTR && j0 + VEC < P.Nj) ? yJ_F[o + VEC] : T(0);
+        if (SCHEME == HYBRID || SCHEME == DOWNWIND) {
+            if (SCHEME == HYBRID) ld_into<T, VEC>(bq + 1, yJ_B + o);
+            else {
+#pragma unroll
+                for (int e = 0; e < VEC + 2; ++e) bq[e] = f[e];
+            }
+            bq[VEC + 1] = (j0 + VEC < P.Nj) ? yJ_B[o + VEC] : T(0);
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const int j = j0 + e;
+            T a, b, m, p;
+            adj_factors<T, SCHEME>(a, b, j, P.Nj, false);
+            if (CTR) adj_operands<T, SCHEME>(m, p, f[e], T(0), T(0), f[e + 2], false);
+            else adj_operands<T, SCHEME>(m, p, f[e], f[e + 1], bq[e + 1], bq[e + 2], false);
+            acc[e] += a * m - b * p;
+        }
+    }
+    if (Z_ON) {
+        const bool fb = P.z_fwd_fallback != 0;
+        const bool up_form = !CTR || fb;   // needs the slot at k itself
+        T f_m[VEC], f_c[VEC], b_c[VEC], b_p[VEC];
+        if (NF) ld_into<T, VEC>(f_m, pl.zf_m + o); else zero_into<T, VEC>(f_m);
+        if (up_form && NF) ld_into<T, VEC>(f_c, pl.y + (long long)C::Z_F * P.sC + o); else zero_into<T, VEC>(f_c);
+        if (!CTR && NB) ld_into<T, VEC>(b_c, pl.y + (long long)C::Z_B * P.sC + o); else zero_into<T, VEC>(b_c);
+        if (NB && !(CTR && fb)) ld_into<T, VEC>(b_p, pl.zb_p + o); else zero_into<T, VEC>(b_p);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            T m, p;
+            adj_operands<T, SCHEME>(m, p, f_m[e], f_c[e], b_c[e], b_p[e], fb);
+            acc[e] += pl.az * m - pl.bz * p;
+        }
+    }
+    if (T_ON) {
+        const bool fb = P.t_fwd_fallback != 0;
+        const bool up_form = !CTR || fb;
+        T f_m[VEC], f_c[VEC], b_c[VEC], b_p[VEC], fac[VEC];
+        if (NF) ld_into<T, VEC>(f_m, pl.tf_m + o); else zero_into<T, VEC>(f_m);
+        if (up_form && NF) ld_into<T, VEC>(f_c, pl.y + (long long)C::T_F * P.sC + o); else zero_into<T, VEC>(f_c);
+        if (!CTR && NB) ld_into<T, VEC>(b_c, pl.y + (long long)C::T_B * P.sC + o); else zero_into<T, VEC>(b_c);
+        if (NB && !(CTR && fb)) ld_into<T, VEC>(b_p, pl.tb_p + o); else zero_into<T, VEC>(b_p);
+        static_factor<T, VEC>(fac, P, i, j0);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            T m, p;
+            adj_operands<T, SCHEME>(m, p, f_m[e], f_c[e], b_c[e], b_p[e], fb);
+            acc[e] += (pl.at * m - pl.bt * p) * fac[e];
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) out[e] = acc[e] * P.inv_div;
+}
+
+// Primal update at one quad.  VARIANT 0: ROF prox + over-relaxation (aux = xbar); 1: README form (aux = y_f).
+// c1 = 1/(1+tau) (rof) or 1/(1+sigma_A) (readme); c2 = theta or sigma_A.  Returns sum (x_new - x0)^2.
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int VARIANT>
+PYTVB_HD T strip_quad_cp_primal(T* x, T* aux, const T* x0, const PrimalPlane<T>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn,
+                                T tau, T c1, T c2) {
+    T dty[VEC];
+    strip_quad_DT<T, VEC, SCHEME, Z_ON, T_ON>(dty, pl, P, i, j0, o, o_up, o_dn);
+    const long long off = pl.img + o;
+    const Pack<T, VEC> xo = ld_pack<T, VEC>(x + off), x0q = ld_pack<T, VEC>(x0 + off);
+    Pack<T, VEC> xn, ax;
+    T fid = T(0);
+    if (VARIANT == 0) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            xn.v[e] = (xo.v[e] - tau * dty[e] + tau * x0q.v[e]) * c1;
+            ax.v[e] = xn.v[e] + c2 * (xn.v[e] - xo.v[e]);
+            const T r = xn.v[e] - x0q.v[e];
+            fid += r * r;
+        }
+    } else {
+        const Pack<T, VEC> yf = ld_pack<T, VEC>(aux + off);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            ax.v[e] = (yf.v[e] + c2 * (xo.v[e] - x0q.v[e])) * c1;
+            xn.v[e] = xo.v[e] - tau * ax.v[e] - tau * dty[e];
+            const T r = xn.v[e] - x0q.v[e];
+            fid += r * r;
+        }
+    }
+    st_pack<T, VEC>(x + off, xn);
+    st_pack<T, VEC>(aux + off, ax);
+    return fid;
+}
+
+}  // namespace pytvb

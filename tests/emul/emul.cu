@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "../../pytv-4d_b200/csrc/host_common.cuh"
+#include "../../pytv-4d_b200/csrc/strip_core.cuh"
 
 namespace pytvb {
 static char g_err[512];
@@ -106,6 +107,44 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct EPrimal {
     }
 };
 
+// generation-2 strip code, walked row by row exactly like cp_dual_strip_kernel / cp_primal_strip_kernel
+template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct EDual2 {
+    static int run(const EArgs<T>& a) {
+        double s = 0;
+        for (int z = 0; z < a.P.Nz; ++z)
+            for (int t = 0; t < a.P.M; ++t) {
+                const DualPlane<T> pl = make_dual_plane<T, SCHEME>(a.X, a.out, a.P, z, t);
+                for (int i = 0; i < a.P.Ni; ++i)
+                    for (int j0 = 0; j0 < a.P.Nj; j0 += VEC) {
+                        const int o = i * a.P.Nj + j0, o_up = i > 0 ? o - a.P.Nj : o, o_dn = i < a.P.Ni - 1 ? o + a.P.Nj : o;
+                        s += (double)strip_quad_cp_dual<T, VEC, SCHEME, Z, TT>(pl, a.P, i, j0, o, o_up, o_dn, a.c0 * a.P.inv_div, T(1) / a.c1);
+                    }
+            }
+        *a.sum = s * (double)a.P.inv_div;
+        return 0;
+    }
+};
+template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct EPrimal2 {
+    static int run(const EArgs<T>& a) {
+        double s = 0;
+        const T c1 = T(1) / (T(1) + (a.variant == 0 ? a.c0 : a.c1));
+        for (int z = 0; z < a.P.Nz; ++z)
+            for (int t = 0; t < a.P.M; ++t) {
+                const PrimalPlane<T> pl = make_primal_plane<T, SCHEME, Z, TT>(a.F, a.P, z, t);
+                for (int i = 0; i < a.P.Ni; ++i)
+                    for (int j0 = 0; j0 < a.P.Nj; j0 += VEC) {
+                        const int o = i * a.P.Nj + j0, o_up = i > 0 ? o - a.P.Nj : o, o_dn = i < a.P.Ni - 1 ? o + a.P.Nj : o;
+                        if (a.variant == 0)
+                            s += (double)strip_quad_cp_primal<T, VEC, SCHEME, Z, TT, 0>(a.out, a.aux, a.x0, pl, a.P, i, j0, o, o_up, o_dn, a.c0, c1, a.c1);
+                        else
+                            s += (double)strip_quad_cp_primal<T, VEC, SCHEME, Z, TT, 1>(a.out, a.aux, a.x0, pl, a.P, i, j0, o, o_up, o_dn, a.c0, c1, a.c1);
+                    }
+            }
+        *a.sum = s;
+        return 0;
+    }
+};
+
 template <typename T> int vec_for(const pytvb_problem* pb, int force_scalar) {
     return (force_scalar || pb->Nj % VecOf<T>::value) ? 1 : VecOf<T>::value;
 }
@@ -135,6 +174,8 @@ int run(int op, const pytvb_problem* pb, const void* in, void* out, void* out2, 
         }
         case 3: a.X = ImgView<T>{(const T*)in, (const T*)lo, (const T*)hi, 1}; return dispatch<EDual, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
         case 4: a.F = FieldView<T>{(const T*)in, (const T*)lo, (const T*)hi}; return dispatch<EPrimal, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
+        case 5: a.X = ImgView<T>{(const T*)in, (const T*)lo, (const T*)hi, 1}; return dispatch<EDual2, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
+        case 6: a.F = FieldView<T>{(const T*)in, (const T*)lo, (const T*)hi}; return dispatch<EPrimal2, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
     }
     return -1;
 }
@@ -142,6 +183,7 @@ int run(int op, const pytvb_problem* pb, const void* in, void* out, void* out2, 
 }  // namespace
 
 // op: 0 D (in=x, out=D) | 1 DT (in=p, out=img) | 2 tv (in=x, out=G, out2=norms|NULL, sum=tv)
+//     5 / 6: generation-2 (strip) code of 3 / 4, same arguments
 //     3 cp_dual (in=xbar, out=y in place, c0=sigma, c1=1/lam, sum=l21) | 4 cp_primal (in=y, out=x, aux, x0, c0=tau, c1=theta|sigma_A, variant)
 extern "C" int pytvb_emulate(int op, const pytvb_problem* pb, const void* in, void* out, void* out2, void* aux, const void* x0, const void* lo,
                              const void* hi, double c0, double c1, int variant, int force_scalar, double* sum) {

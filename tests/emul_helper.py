@@ -17,7 +17,7 @@ from pytv_b200 import _lib  # noqa: E402
 
 def build_emul(force=False):
     src = os.path.join(EMUL_DIR, "emul.cu")
-    deps = [src] + [os.path.join(ROOT, "pytv-4d_b200", "csrc", f) for f in ("tv_core.cuh", "kernels.cuh", "host_common.cuh")]
+    deps = [src] + [os.path.join(ROOT, "pytv-4d_b200", "csrc", f) for f in ("tv_core.cuh", "strip_core.cuh", "kernels.cuh", "kernels2.cuh", "host_common.cuh")]
     if not force and os.path.exists(EMUL_SO) and all(os.path.getmtime(EMUL_SO) >= os.path.getmtime(d) for d in deps):
         return EMUL_SO
     cmd = ["nvcc", "-O1", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "--extended-lambda", "-gencode",
@@ -97,19 +97,24 @@ def tv(x, scheme, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_re
     return val, G, norms
 
 
+GEN = 1   # 1: tv_core.cuh quad code, 2: strip_core.cuh (module-level switch used by the tests)
+
+
 def cp_dual(xbar, y, scheme, lam, sigma, lo=None, hi=None, z_offset=0, Nz_global=None, scalar=False, **w):
     pb, keep = _problem(scheme, xbar.dtype, xbar.shape, w.get("reg_z_over_reg", 1.0), w.get("reg_time", 0.0), w.get("mask_static", False),
                         w.get("factor_reg_static", 0.0), z_offset, Nz_global)
-    return _call(3, pb, np.ascontiguousarray(xbar), y, lo=lo, hi=hi, c0=sigma, c1=1.0 / lam, scalar=scalar)
+    return _call(3 if GEN == 1 else 5, pb, np.ascontiguousarray(xbar), y, lo=lo, hi=hi, c0=sigma, c1=1.0 / lam, scalar=scalar)
 
 
 def cp_primal(y, x, aux, x0, scheme, tau, c2, variant, lo=None, hi=None, z_offset=0, Nz_global=None, scalar=False, **w):
     pb, keep = _problem(scheme, x.dtype, x.shape, w.get("reg_z_over_reg", 1.0), w.get("reg_time", 0.0), w.get("mask_static", False),
                         w.get("factor_reg_static", 0.0), z_offset, Nz_global)
-    return _call(4, pb, np.ascontiguousarray(y), x, aux=aux, x0=x0, lo=lo, hi=hi, c0=tau, c1=c2, variant=variant, scalar=scalar)
+    return _call(4 if GEN == 1 else 6, pb, np.ascontiguousarray(y), x, aux=aux, x0=x0, lo=lo, hi=hi, c0=tau, c1=c2, variant=variant, scalar=scalar)
 
 
 class EmulOps:
+    gen = 2
+
     """Executor for pytv_b200.cp.CPSolver that runs the per-quad CUDA code on the host (CPU tensors).
     Lets the multi-rank slab / halo / all-reduce logic be tested with the gloo backend."""
 
@@ -119,7 +124,7 @@ class EmulOps:
 
     def cp_dual(self, pb, xbar, y, lam, sigma, d_l21, lo, hi, ws):
         s = ctypes.c_double(0.0)
-        rc = emul().pytvb_emulate(3, ctypes.byref(pb), self._p(xbar), self._p(y), None, None, None, self._p(lo), self._p(hi), sigma, 1.0 / lam, 0, 0,
+        rc = emul().pytvb_emulate(3 if self.gen == 1 else 5, ctypes.byref(pb), self._p(xbar), self._p(y), None, None, None, self._p(lo), self._p(hi), sigma, 1.0 / lam, 0, 0,
                                   ctypes.byref(s))
         assert rc == 0
         if d_l21 is not None:
@@ -127,7 +132,7 @@ class EmulOps:
 
     def cp_primal(self, variant, pb, y, x, aux, x0, tau, c2, d_fid, lo, hi, ws):
         s = ctypes.c_double(0.0)
-        rc = emul().pytvb_emulate(4, ctypes.byref(pb), self._p(y), self._p(x), None, self._p(aux), self._p(x0), self._p(lo), self._p(hi), tau, c2,
+        rc = emul().pytvb_emulate(4 if self.gen == 1 else 6, ctypes.byref(pb), self._p(y), self._p(x), None, self._p(aux), self._p(x0), self._p(lo), self._p(hi), tau, c2,
                                   0 if variant == "rof" else 1, 0, ctypes.byref(s))
         assert rc == 0
         if d_fid is not None:

@@ -91,9 +91,18 @@ def test_slabs_with_halos_reproduce_whole_volume(scheme, split):
     assert tv_sum == pytest.approx(tv, rel=1e-13)
 
 
+@pytest.fixture(params=[1, 2], ids=["gen1", "gen2"])
+def gen(request):
+    """Both kernel generations of the CP passes (tv_core.cuh quad code, strip_core.cuh strip code)."""
+    old = em.GEN
+    em.GEN = request.param
+    yield request.param
+    em.GEN = old
+
+
 @pytest.mark.parametrize("scheme", SCHEMES)
 @pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
-def test_cp_iterations_match_oracle(scheme, dtype, golden_kat):
+def test_cp_iterations_match_oracle(scheme, dtype, golden_kat, gen):
     g = golden_kat["cp_small4d"][scheme]
     x0 = cases.cp_volume().astype(dtype)
     kw = dict(reg_z_over_reg=0.5, reg_time=2 ** -5, mask_static=cases.cp_mask_static(), factor_reg_static=4.0)
@@ -123,8 +132,41 @@ def test_cp_iterations_match_oracle(scheme, dtype, golden_kat):
     assert x[1, 1, 3, 4] == pytest.approx(g["rof_x_probe"], rel=1e-11 if dtype == np.float64 else 1e-4)
 
 
+@pytest.mark.parametrize("shape", [(3, 2, 5, 8), (2, 3, 6, 4), (1, 1, 7, 12), (5, 1, 4, 8), (1, 4, 3, 4), (2, 2, 1, 4), (3, 3, 2, 8)],
+                         ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("scheme", SCHEMES)
-def test_cp_slabs(scheme):
+def test_cp_single_iteration_all_shapes(scheme, shape, gen):
+    """One iteration from a random state (non-zero y everywhere, also at the structurally-zero positions that
+    the adjoint must ignore) on small and degenerate shapes; weights and mask_static on."""
+    rs = np.random.RandomState(31)
+    Nz, M, Ni, Nj = shape
+    x0 = rs.rand(*shape)
+    ms = rs.rand(1, 1, Ni, Nj) > 0.5
+    kw = dict(reg_z_over_reg=0.6, reg_time=0.4, mask_static=ms, factor_reg_static=3.0)
+    Nd = orc.num_components(scheme, Nz, M, 0.6, 0.4)
+    y = 0.2 * rs.randn(Nz, Nd, M, Ni, Nj)
+    x = x0 + 0.1 * rs.randn(*shape)
+    xbar = x + 0.01 * rs.randn(*shape)
+    for variant in (0, 1):
+        if variant == 0:
+            x_ref, aux_ref, y_ref, e_ref = orc.cp_rof_step(x.copy(), xbar.copy(), x0, y.copy(), scheme, lam=0.1, sigma=0.5, tau=0.07, theta=0.9, **kw)
+            yy, xx, aux = y.copy(), x.copy(), xbar.copy()
+            l21 = em.cp_dual(xbar, yy, scheme, 0.1, 0.5, **kw)
+            fid = em.cp_primal(yy, xx, aux, x0, scheme, 0.07, 0.9, 0, **kw)
+        else:
+            y_f = 0.1 * rs.randn(*shape)
+            x_ref, aux_ref, y_ref, e_ref = orc.cp_readme_step(x.copy(), x0, y_f.copy(), y.copy(), scheme, lam=0.1, sigma_D=0.5, sigma_A=0.8, tau=0.07, **kw)
+            yy, xx, aux = y.copy(), x.copy(), y_f.copy()
+            l21 = em.cp_dual(x, yy, scheme, 0.1, 0.5, **kw)
+            fid = em.cp_primal(yy, xx, aux, x0, scheme, 0.07, 0.8, 1, **kw)
+        np.testing.assert_allclose(yy, y_ref, atol=1e-13)
+        np.testing.assert_allclose(xx, x_ref, atol=1e-13)
+        np.testing.assert_allclose(aux, aux_ref, atol=1e-13)
+        assert 0.5 * fid + 0.1 * l21 == pytest.approx(e_ref, rel=1e-12)
+
+
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_cp_slabs(scheme, gen):
     """One CP iteration computed slab by slab with halos equals the whole-volume iteration."""
     rs = np.random.RandomState(4)
     Nz, M, N = 5, 2, 8

@@ -293,9 +293,56 @@ def test_non_square_and_unaligned_paths():
 
 
 # ------------------------------------------------------------------ Chambolle-Pock
+@pytest.fixture(params=["1", "2"], ids=["gen1", "gen2"])
+def gen(request):
+    """Both kernel generations of the CP passes (PYTVB_GEN is read by the library at every call)."""
+    import os
+    old = os.environ.get("PYTVB_GEN")
+    os.environ["PYTVB_GEN"] = request.param
+    yield request.param
+    if old is None:
+        del os.environ["PYTVB_GEN"]
+    else:
+        os.environ["PYTVB_GEN"] = old
+
+
+@pytest.mark.parametrize("shape", [(3, 2, 5, 8), (2, 3, 6, 4), (1, 1, 7, 12), (5, 1, 4, 8), (1, 4, 3, 4), (2, 2, 1, 4), (3, 3, 2, 8), (4, 2, 33, 260)],
+                         ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_cp_single_iteration_all_shapes(scheme, shape, gen):
+    """One iteration from a random state (y non-zero also at the structurally-zero positions the adjoint must
+    ignore) on small, degenerate and multi-CTA shapes; weights and mask_static on; float64 against the oracle."""
+    lib = _lib.lib()
+    rs = np.random.RandomState(31)
+    Nz, M, Ni, Nj = shape
+    x0 = rs.rand(*shape)
+    ms = rs.rand(1, 1, Ni, Nj) > 0.5
+    kw = dict(reg_z_over_reg=0.6, reg_time=0.4, mask_static=ms, factor_reg_static=3.0)
+    Nd = orc.num_components(scheme, Nz, M, 0.6, 0.4)
+    y = 0.2 * rs.randn(Nz, Nd, M, Ni, Nj)
+    x = x0 + 0.1 * rs.randn(*shape)
+    xbar = x + 0.01 * rs.randn(*shape)
+    y_f = 0.1 * rs.randn(*shape)
+    for variant in ("rof", "readme"):
+        s = pytv.CPSolver(x0, lam=0.1, scheme=scheme, variant=variant, sigma=0.5, tau=0.07, theta=0.9, sigma_A=0.8, **kw)
+        s.x.copy_(torch.as_tensor(x))
+        s.y.copy_(torch.as_tensor(y))
+        if variant == "rof":
+            s.aux.copy_(torch.as_tensor(xbar))
+            x_ref, aux_ref, y_ref, e_ref = orc.cp_rof_step(x.copy(), xbar.copy(), x0, y.copy(), scheme, lam=0.1, sigma=0.5, tau=0.07, theta=0.9, **kw)
+        else:
+            s.aux.copy_(torch.as_tensor(y_f))
+            x_ref, aux_ref, y_ref, e_ref = orc.cp_readme_step(x.copy(), x0, y_f.copy(), y.copy(), scheme, lam=0.1, sigma_D=0.5, sigma_A=0.8, tau=0.07, **kw)
+        s.step()
+        np.testing.assert_allclose(s.y.cpu().numpy(), y_ref, atol=1e-12)
+        np.testing.assert_allclose(s.x.cpu().numpy(), x_ref, atol=1e-12)
+        np.testing.assert_allclose(s.aux.cpu().numpy(), aux_ref, atol=1e-12)
+        assert s.energy() == pytest.approx(e_ref, rel=1e-12)
+
+
 @pytest.mark.parametrize("scheme", SCHEMES)
 @pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
-def test_cp_small4d_golden(scheme, dtype, golden_kat):
+def test_cp_small4d_golden(scheme, dtype, golden_kat, gen):
     g = golden_kat["cp_small4d"][scheme]
     x0 = cases.cp_volume().astype(dtype)
     kw = dict(reg_z_over_reg=0.5, reg_time=2 ** -5, mask_static=cases.cp_mask_static(), factor_reg_static=4.0)
@@ -318,6 +365,24 @@ def test_cp_small4d_golden(scheme, dtype, golden_kat):
     assert x.sum(dtype=np.float64) == pytest.approx(g["rof_sum_x"], rel=rel)
     assert float(s.aux.sum(dtype=torch.float64)) == pytest.approx(g["rof_sum_xbar"], rel=rel)
     assert x[1, 1, 3, 4] == pytest.approx(g["rof_x_probe"], rel=1e-11 if dtype == np.float64 else 1e-4)
+
+
+def test_cp_generations_agree_float32():
+    """gen-1 (exact sqrt / division) and gen-2 (rsqrt, reciprocal) float32 kernels stay within 1e-6 of each other
+    over 20 iterations on a 4-D volume large enough for many CTAs."""
+    import os
+    torch.manual_seed(4)
+    x0 = torch.rand(6, 3, 64, 128, device="cuda")
+    res = {}
+    for g in ("1", "2"):
+        os.environ["PYTVB_GEN"] = g
+        s = pytv.CPSolver(x0, lam=0.1, scheme="hybrid", variant="rof", reg_time=2 ** -5)
+        s.step(20)
+        res[g] = (s.x.clone(), s.y.clone(), s.energy())
+    del os.environ["PYTVB_GEN"]
+    assert float((res["1"][0] - res["2"][0]).abs().max()) < 1e-5
+    assert float((res["1"][1] - res["2"][1]).abs().max()) < 1e-5
+    assert res["1"][2] == pytest.approx(res["2"][2], rel=1e-6)
 
 
 def test_cp_and_gd_loops_synthetic(golden_kat):
