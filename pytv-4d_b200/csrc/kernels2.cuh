@@ -19,9 +19,9 @@ namespace pytvb {
 
 // Base tiling over strips: Ni is replaced by the number of R-row strips.
 template <int R>
-inline Tiling make_strip_tiling(int Nj, int Ni, int M, int nz, int vec) {
+inline Tiling make_strip_tiling(int Nj, int Ni, int M, int nz, int vec, int z_lo = 0) {
     const int nstrips = (Ni + R - 1) / R;
-    Tiling t = make_tiling(Nj, nstrips, M, 0, nz, vec);
+    Tiling t = make_tiling(Nj, nstrips, M, z_lo, nz, vec);
     // keep a band at about BAND_ROWS image rows
     int rb = BAND_ROWS / (t.TR * R);
     if (rb < 1) rb = 1;
@@ -82,6 +82,104 @@ __global__ void __launch_bounds__(CTA_THREADS, PYTVB_PRIMAL_MINB) cp_primal_stri
         const double bs = block_sum((double)fid);
         if (threadIdx.x == 0) partial[blockIdx.x] = bs;
     }
+}
+
+// Row loop shared by every strip kernel: calls f(i, o, o_up, o_dn) for the R rows of this thread's strip.
+template <int R, typename F>
+__device__ __forceinline__ void for_strip_rows(const QuadIdx& q, int Ni, int Nj, F f) {
+    const int i0 = q.i * R;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = i0 + r;
+        if (i < Ni) {
+            const int o = i * Nj + q.j0;
+            f(i, o, i > 0 ? o - Nj : o, i < Ni - 1 ? o + Nj : o);
+        }
+    }
+}
+
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R>
+__global__ void __launch_bounds__(CTA_THREADS) D_strip_kernel(ImgView<T> X, T* __restrict__ D, Params<T> P, Tiling tl) {
+    const QuadIdx q = decode_quad(tl, (P.Ni + R - 1) / R, VEC);
+    if (!q.active) return;
+    const DualPlane<T> pl = make_dual_plane<T, SCHEME>(X, D, P, q.z, q.t);   // pl.y = component 0 of D at plane (z, t)
+    for_strip_rows<R>(q, P.Ni, P.Nj, [&](int i, int o, int o_up, int o_dn) {
+        strip_quad_D<T, VEC, SCHEME, Z_ON, T_ON>(pl.y, pl, P, i, q.j0, o, o_up, o_dn);
+    });
+}
+
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R>
+__global__ void __launch_bounds__(CTA_THREADS) DT_strip_kernel(FieldView<T> Pf, T* __restrict__ out, Params<T> P, Tiling tl) {
+    const QuadIdx q = decode_quad(tl, (P.Ni + R - 1) / R, VEC);
+    if (!q.active) return;
+    const PrimalPlane<T> pl = make_primal_plane<T, SCHEME, Z_ON, T_ON>(Pf, P, q.z, q.t);
+    for_strip_rows<R>(q, P.Ni, P.Nj, [&](int i, int o, int o_up, int o_dn) {
+        T v[VEC];
+        strip_quad_DT<T, VEC, SCHEME, Z_ON, T_ON>(v, pl, P, i, q.j0, o, o_up, o_dn);
+        Pack<T, VEC> pk;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) pk.v[e] = v[e];
+        st_pack<T, VEC>(out + pl.img + o, pk);
+    });
+}
+
+template <typename T, int VEC, int R>
+__global__ void __launch_bounds__(CTA_THREADS) l21_strip_kernel(const T* __restrict__ D, int Nd, T* __restrict__ norms, double* __restrict__ partial,
+                                                                Params<T> P, Tiling tl) {
+    const QuadIdx q = decode_quad(tl, (P.Ni + R - 1) / R, VEC);
+    T sum = T(0);
+    if (q.active) {
+        const T* base = D + (long long)q.z * P.sZf + (long long)q.t * P.sT;
+        T* nbase = norms ? norms + (long long)q.z * P.sZ + (long long)q.t * P.sT : nullptr;
+        for_strip_rows<R>(q, P.Ni, P.Nj, [&](int, int o, int, int) {
+            T s[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) s[e] = T(0);
+            for (int k = 0; k < Nd; ++k) {
+                const Pack<T, VEC> v = ld_pack<T, VEC>(base + (long long)k * P.sC + o);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) s[e] += v.v[e] * v.v[e];
+            }
+            Pack<T, VEC> nr;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                nr.v[e] = pytvb_sqrt(s[e]);
+                sum += nr.v[e];
+            }
+            if (nbase) st_pack<T, VEC>(nbase + o, nr);
+        });
+    }
+    const double bs = block_sum((double)sum);
+    if (threadIdx.x == 0) partial[blockIdx.x] = bs;
+}
+
+// TV sweep 1 (strip form): z range tl.z_lo .. tl.z_lo+tl.nz-1 includes one halo plane per side when present.
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R>
+__global__ void __launch_bounds__(CTA_THREADS) tv_norm_strip_kernel(ImgView<T> X, T* __restrict__ Wz0, T* __restrict__ norms, double* __restrict__ partial,
+                                                                    Params<T> P, Tiling tl) {
+    const QuadIdx q = decode_quad(tl, (P.Ni + R - 1) / R, VEC);
+    T sum = T(0);
+    if (q.active) {
+        const DualPlane<T> pl = make_dual_plane<T, SCHEME>(X, Wz0, P, q.z, q.t);
+        const long long img = (long long)q.z * P.sZ + (long long)q.t * P.sT;
+        const bool own = q.z >= 0 && q.z < P.Nz;
+        T* np = (norms && own) ? norms + img : nullptr;
+        for_strip_rows<R>(q, P.Ni, P.Nj, [&](int i, int o, int o_up, int o_dn) {
+            const T v = strip_quad_tv_norm<T, VEC, SCHEME, Z_ON, T_ON>(Wz0 + img, np, pl, P, i, q.j0, o, o_up, o_dn);
+            if (own) sum += v;
+        });
+    }
+    const double bs = block_sum((double)sum);
+    if (threadIdx.x == 0) partial[blockIdx.x] = bs;
+}
+
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R>
+__global__ void __launch_bounds__(CTA_THREADS) tv_grad_strip_kernel(ImgView<T> X, ImgView<T> W, T* __restrict__ G, Params<T> P, Tiling tl) {
+    const QuadIdx q = decode_quad(tl, (P.Ni + R - 1) / R, VEC);
+    if (!q.active) return;
+    const GradPlane<T> pl = make_grad_plane<T, SCHEME>(X, W, P, q.z, q.t);
+    T* gp = G + (long long)q.z * P.sZ + (long long)q.t * P.sT;
+    for_strip_rows<R>(q, P.Ni, P.Nj, [&](int i, int o, int, int) { strip_quad_G<T, VEC, SCHEME, Z_ON, T_ON>(gp, pl, P, i, q.j0, o); });
 }
 
 }  // namespace pytvb

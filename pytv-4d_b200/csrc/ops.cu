@@ -1,13 +1,36 @@
 // Operator entry points: D, D_T, L21, mask.
+#include <stdlib.h>
+
 #include "host_common.cuh"
+#include "kernels2.cuh"
+
+#ifndef PYTVB_STRIP_R
+#define PYTVB_STRIP_R 4
+#endif
 
 using namespace pytvb;
 
 namespace {
 
+bool use_gen2() {
+    const char* e = getenv("PYTVB_GEN");
+    return !e || atoi(e) >= 2;
+}
+
 template <typename T> struct DArgs { ImgView<T> X; T* D; Params<T> P; int vec; cudaStream_t st; };
 template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchD {
     static int run(const DArgs<T>& a) {
+        if constexpr (VEC > 1) {
+            if (use_gen2()) {
+                constexpr int R = PYTVB_STRIP_R;
+                const Tiling tl = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.P.Nz, VEC);
+                if (int rc = check_grid(tl)) return rc;
+                D_strip_kernel<T, VEC, SCHEME, Z, TT, R><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.D, a.P, tl);
+                count_launches(1);
+                PYTVB_CUDA(cudaGetLastError());
+                return PYTVB_OK;
+            }
+        }
         const Tiling tl = make_tiling(a.P.Nj, a.P.Ni, a.P.M, 0, a.P.Nz, VEC);
         if (int rc = check_grid(tl)) return rc;
         D_kernel<T, VEC, SCHEME, Z, TT><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.D, a.P, tl);
@@ -20,6 +43,17 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchD {
 template <typename T> struct DTArgs { FieldView<T> F; T* out; Params<T> P; cudaStream_t st; };
 template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchDT {
     static int run(const DTArgs<T>& a) {
+        if constexpr (VEC > 1) {
+            if (use_gen2()) {
+                constexpr int R = PYTVB_STRIP_R;
+                const Tiling tl = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.P.Nz, VEC);
+                if (int rc = check_grid(tl)) return rc;
+                DT_strip_kernel<T, VEC, SCHEME, Z, TT, R><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.F, a.out, a.P, tl);
+                count_launches(1);
+                PYTVB_CUDA(cudaGetLastError());
+                return PYTVB_OK;
+            }
+        }
         const Tiling tl = make_tiling(a.P.Nj, a.P.Ni, a.P.M, 0, a.P.Nz, VEC);
         if (int rc = check_grid(tl)) return rc;
         DT_kernel<T, VEC, SCHEME, Z, TT><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.F, a.out, a.P, tl);
@@ -58,9 +92,18 @@ int run_l21(const pytvb_problem* pb, const void* D, int Nd, void* norms, double*
     Params<T> P = make_params<T>(pb);
     P.sZf = P.sC * Nd;
     const int vec = pick_vec<T>(pb, {D, norms});
+    double* partial = (double*)ws;
+    if (vec > 1 && use_gen2()) {
+        constexpr int R = PYTVB_STRIP_R;
+        const Tiling tl = make_strip_tiling<R>(P.Nj, P.Ni, P.M, P.Nz, vec);
+        if (int rc = check_grid(tl)) return rc;
+        l21_strip_kernel<T, VecOf<T>::value, R><<<(unsigned)tl.nblocks, CTA_THREADS, 0, st>>>((const T*)D, Nd, (T*)norms, partial, P, tl);
+        count_launches(1);
+        PYTVB_CUDA(cudaGetLastError());
+        return finalize_sum(partial, tl.nblocks, d_sum, st);
+    }
     const Tiling tl = make_tiling(P.Nj, P.Ni, P.M, 0, P.Nz, vec);
     if (int rc = check_grid(tl)) return rc;
-    double* partial = (double*)ws;
     if (vec == 1)
         l21_kernel<T, 1><<<(unsigned)tl.nblocks, CTA_THREADS, 0, st>>>((const T*)D, Nd, (T*)norms, partial, P, tl);
     else

@@ -68,16 +68,12 @@ PYTVB_HD DualPlane<T> make_dual_plane(const ImgView<T>& X, T* y, const Params<T>
     return d;
 }
 
-// One quad of the dual pass.  o = i*Nj + j0; o_up / o_dn = offsets of rows i-1 / i+1 clamped to [0, Ni).
-// sig = sigma * inv_div (so that y + sigma*D = y + sig*raw_difference).  Returns sum_e sqrt(sum_k raw_k^2)
-// (the caller multiplies the total by inv_div to get L21(D xbar)).
+// Raw differences of one quad: d[k][e] = weight * (x[k+1] - x[k]) etc. WITHOUT the scheme's global divisor.
+// o = i*Nj + j0; o_up / o_dn = offsets of rows i-1 / i+1 clamped to [0, Ni).
 template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON>
-PYTVB_HD T strip_quad_cp_dual(const DualPlane<T>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn, T sig, T lam) {
+PYTVB_HD void strip_raw_diffs(T (*d)[VEC], const DualPlane<T>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn) {
     typedef Comp<SCHEME, Z_ON, T_ON> C;
-    constexpr int ND = C::ND;
-    T c[VEC + 2], up[VEC], dn[VEC], zm[VEC], zp[VEC], tm[VEC], tp[VEC], y[ND][VEC], d[ND][VEC];
-#pragma unroll
-    for (int k = 0; k < ND; ++k) ld_into<T, VEC>(y[k], pl.y + (long long)k * P.sC + o);
+    T c[VEC + 2], up[VEC], dn[VEC], zm[VEC], zp[VEC], tm[VEC], tp[VEC];
     ld_into<T, VEC>(c + 1, pl.c + o);
     c[0] = (C::NEED_BWD && j0 > 0) ? pl.c[o - 1] : c[1];
     c[VEC + 1] = (C::NEED_FWD && j0 + VEC < P.Nj) ? pl.c[o + VEC] : c[VEC];
@@ -91,7 +87,6 @@ PYTVB_HD T strip_quad_cp_dual(const DualPlane<T>& pl, const Params<T>& P, int i,
     if (T_ON) static_factor<T, VEC>(fac, P, i, j0);
     // centred scheme: in-plane factors (rows: uniform per row; columns: only the volume's first / last column)
     const T fi = (SCHEME == CENTRAL) ? ((i > 0 && i < P.Ni - 1) ? T(1) : T(0)) : T(1);
-    T l21 = T(0);
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
         const T x = c[e + 1];
@@ -120,6 +115,22 @@ PYTVB_HD T strip_quad_cp_dual(const DualPlane<T>& pl, const Params<T>& P, int i,
             if (Z_ON) d[C::Z_F][e] = (P.srz * pl.fz) * (zp[e] - zm[e]);
             if (T_ON) d[C::T_F][e] = (P.srt * pl.ft * fac[e]) * (tp[e] - tm[e]);
         }
+    }
+}
+
+// One quad of the dual pass.  sig = sigma * inv_div (so that y + sigma*D = y + sig*raw_difference).
+// Returns sum_e sqrt(sum_k raw_k^2) (the caller multiplies the total by inv_div to get L21(D xbar)).
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON>
+PYTVB_HD T strip_quad_cp_dual(const DualPlane<T>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn, T sig, T lam) {
+    typedef Comp<SCHEME, Z_ON, T_ON> C;
+    constexpr int ND = C::ND;
+    T y[ND][VEC], d[ND][VEC];
+#pragma unroll
+    for (int k = 0; k < ND; ++k) ld_into<T, VEC>(y[k], pl.y + (long long)k * P.sC + o);
+    strip_raw_diffs<T, VEC, SCHEME, Z_ON, T_ON>(d, pl, P, i, j0, o, o_up, o_dn);
+    T l21 = T(0);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
         T s = T(0), sd = T(0);
 #pragma unroll
         for (int k = 0; k < ND; ++k) {
@@ -142,6 +153,46 @@ PYTVB_HD T strip_quad_cp_dual(const DualPlane<T>& pl, const Params<T>& P, int i,
         st_pack<T, VEC>(pl.y + (long long)k * P.sC + o, pk);
     }
     return l21;
+}
+
+// D_scheme at one quad, stored to the field plane `out` (component 0 of plane (z,t); component k at + k*sC).
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON>
+PYTVB_HD void strip_quad_D(T* out, const DualPlane<T>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn) {
+    typedef Comp<SCHEME, Z_ON, T_ON> C;
+    T d[C::ND][VEC];
+    strip_raw_diffs<T, VEC, SCHEME, Z_ON, T_ON>(d, pl, P, i, j0, o, o_up, o_dn);
+#pragma unroll
+    for (int k = 0; k < C::ND; ++k) {
+        Pack<T, VEC> pk;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) pk.v[e] = d[k][e] * P.inv_div;
+        st_pack<T, VEC>(out + (long long)k * P.sC + o, pk);
+    }
+}
+
+// TV sweep 1 at one quad: w = 1/|D x| (0 where the norm is 0) into `w_plane`, optional norms (inf where 0)
+// into `n_plane`; returns the sum of the norms.  |D x| = inv_div * sqrt(sum raw^2).
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON>
+PYTVB_HD T strip_quad_tv_norm(T* w_plane, T* n_plane, const DualPlane<T>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn) {
+    typedef Comp<SCHEME, Z_ON, T_ON> C;
+    T d[C::ND][VEC];
+    strip_raw_diffs<T, VEC, SCHEME, Z_ON, T_ON>(d, pl, P, i, j0, o, o_up, o_dn);
+    Pack<T, VEC> w, n;
+    T sum = T(0);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        T s = T(0);
+#pragma unroll
+        for (int k = 0; k < C::ND; ++k) s += d[k][e] * d[k][e];
+        const T rs = fast_rsqrt(s);                 // inf for s == 0
+        const T nr = s > T(0) ? s * rs * P.inv_div : T(0);
+        w.v[e] = s > T(0) ? rs * P.div : T(0);
+        n.v[e] = s > T(0) ? nr : T(INFINITY);
+        sum += nr;
+    }
+    st_pack<T, VEC>(w_plane + o, w);
+    if (n_plane) st_pack<T, VEC>(n_plane + o, n);
+    return sum;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -329,6 +380,123 @@ PYTVB_HD T strip_quad_cp_primal(T* x, T* aux, const T* x0, const PrimalPlane<T>&
     st_pack<T, VEC>(x + off, xn);
     st_pack<T, VEC>(aux + off, ax);
     return fid;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TV sweep 2 (sub-gradient from x and w = 1/|D x|), strip addressing.  See g_axis in tv_core.cuh for the rule.
+template <typename T>
+struct GradPlane {
+    const T* x;  const T* xzm;  const T* xzp;  const T* xtm;  const T* xtp;    // image planes, clamped
+    const T* xzm2; const T* xzp2; const T* xtm2; const T* xtp2;                  // centred scheme: distance 2
+    const T* w;  const T* wzm;  const T* wzp;  const T* wtm;  const T* wtp;    // inverse-norm planes, clamped
+    T az, bz, at, bt;      // centred scheme: weight * existence of the minus / plus term; other schemes: weight
+    bool z_fb, t_fb;       // centred scheme on a length-2 axis -> forward rule
+};
+
+template <typename T, int SCHEME>
+PYTVB_HD GradPlane<T> make_grad_plane(const ImgView<T>& X, const ImgView<T>& W, const Params<T>& P, int z, int t) {
+    GradPlane<T> g;
+    const long long zg = P.zg0 + z;
+    const bool v_zm = zg > 0, v_zp = zg < P.NzG - 1, v_tm = t > 0, v_tp = t < P.M - 1;
+    g.x = X.row(P, z, t, 0);
+    g.w = W.row(P, z, t, 0);
+    g.xzm = v_zm ? X.row(P, z - 1, t, 0) : g.x;  g.wzm = v_zm ? W.row(P, z - 1, t, 0) : g.w;
+    g.xzp = v_zp ? X.row(P, z + 1, t, 0) : g.x;  g.wzp = v_zp ? W.row(P, z + 1, t, 0) : g.w;
+    g.xtm = v_tm ? X.row(P, z, t - 1, 0) : g.x;  g.wtm = v_tm ? W.row(P, z, t - 1, 0) : g.w;
+    g.xtp = v_tp ? X.row(P, z, t + 1, 0) : g.x;  g.wtp = v_tp ? W.row(P, z, t + 1, 0) : g.w;
+    g.xzm2 = g.xzp2 = g.xtm2 = g.xtp2 = g.x;
+    g.az = g.bz = P.srz;
+    g.at = g.bt = P.srt;
+    g.z_fb = P.z_fwd_fallback != 0;
+    g.t_fb = P.t_fwd_fallback != 0;
+    if (SCHEME == CENTRAL) {
+        if (!g.z_fb) {
+            if (zg >= 2) g.xzm2 = X.row(P, z - 2, t, 0); else g.az = T(0);
+            if (zg <= P.NzG - 3) g.xzp2 = X.row(P, z + 2, t, 0); else g.bz = T(0);
+        }
+        if (!g.t_fb) {
+            if (t >= 2) g.xtm2 = X.row(P, z, t - 2, 0); else g.at = T(0);
+            if (t <= P.M - 3) g.xtp2 = X.row(P, z, t + 2, 0); else g.bt = T(0);
+        }
+    }
+    return g;
+}
+
+// One axis of the sub-gradient with clamped neighbours: the one-sided and hybrid rules vanish by themselves
+// at the boundary ((x_k - x_k) = 0); the centred rule takes explicit 0/1 factors a, b.
+template <typename T, int SCHEME>
+PYTVB_HD T strip_g_axis(bool fallback, T a, T b, T xm2, T xm, T xc, T xp, T xp2, T wm, T wc, T wp) {
+    if (SCHEME == UPWIND || (SCHEME == CENTRAL && fallback)) return (xc - xm) * wm - (xp - xc) * wc;
+    if (SCHEME == DOWNWIND) return (xc - xm) * wc - (xp - xc) * wp;
+    if (SCHEME == HYBRID) return (xc - xm) * (wm + wc) - (xp - xc) * (wc + wp);
+    return a * ((xc - xm2) * wm) - b * ((xp2 - xc) * wp);
+}
+
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON>
+PYTVB_HD void strip_quad_G(T* g_plane, const GradPlane<T>& pl, const Params<T>& P, int i, int j0, int o) {
+    constexpr bool CEN = (SCHEME == CENTRAL);
+    const int Nj = P.Nj;
+    const int o_up = i > 0 ? o - Nj : o, o_dn = i < P.Ni - 1 ? o + Nj : o;
+    // ---- columns: x with 2 and w with 1 element on each side (clamped)
+    T xr[VEC + 4], wr[VEC + 2];
+    ld_into<T, VEC>(xr + 2, pl.x + o);
+    ld_into<T, VEC>(wr + 1, pl.w + o);
+    xr[1] = j0 > 0 ? pl.x[o - 1] : xr[2];
+    wr[0] = j0 > 0 ? pl.w[o - 1] : wr[1];
+    xr[VEC + 2] = j0 + VEC < Nj ? pl.x[o + VEC] : xr[VEC + 1];
+    wr[VEC + 1] = j0 + VEC < Nj ? pl.w[o + VEC] : wr[VEC];
+    xr[0] = (CEN && j0 > 1) ? pl.x[o - 2] : xr[1];
+    xr[VEC + 3] = (CEN && j0 + VEC + 1 < Nj) ? pl.x[o + VEC + 1] : xr[VEC + 2];
+    T g[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        const int j = j0 + e;
+        const T a = (CEN && j < 2) ? T(0) : T(1), b = (CEN && j > Nj - 3) ? T(0) : T(1);
+        g[e] = strip_g_axis<T, SCHEME>(false, a, b, xr[e], xr[e + 1], xr[e + 2], xr[e + 3], xr[e + 4], wr[e], wr[e + 1], wr[e + 2]);
+    }
+    // ---- rows
+    {
+        T xm[VEC], xp[VEC], wm[VEC], wp[VEC], xm2[VEC], xp2[VEC];
+        ld_into<T, VEC>(xm, pl.x + o_up);  ld_into<T, VEC>(xp, pl.x + o_dn);
+        ld_into<T, VEC>(wm, pl.w + o_up);  ld_into<T, VEC>(wp, pl.w + o_dn);
+        T a = T(1), b = T(1);
+        if (CEN) {
+            ld_into<T, VEC>(xm2, pl.x + (i > 1 ? o - 2 * Nj : o));
+            ld_into<T, VEC>(xp2, pl.x + (i < P.Ni - 2 ? o + 2 * Nj : o));
+            a = i >= 2 ? T(1) : T(0);
+            b = i <= P.Ni - 3 ? T(1) : T(0);
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e)
+            g[e] += strip_g_axis<T, SCHEME>(false, a, b, CEN ? xm2[e] : T(0), xm[e], xr[e + 2], xp[e], CEN ? xp2[e] : T(0), wm[e], wr[e + 1], wp[e]);
+    }
+    if (Z_ON) {
+        T xm[VEC], xp[VEC], wm[VEC], wp[VEC], xm2[VEC], xp2[VEC];
+        ld_into<T, VEC>(xm, pl.xzm + o);  ld_into<T, VEC>(xp, pl.xzp + o);
+        ld_into<T, VEC>(wm, pl.wzm + o);  ld_into<T, VEC>(wp, pl.wzp + o);
+        if (CEN) { ld_into<T, VEC>(xm2, pl.xzm2 + o); ld_into<T, VEC>(xp2, pl.xzp2 + o); }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const T v = strip_g_axis<T, SCHEME>(pl.z_fb, pl.az, pl.bz, CEN ? xm2[e] : T(0), xm[e], xr[e + 2], xp[e], CEN ? xp2[e] : T(0), wm[e], wr[e + 1], wp[e]);
+            g[e] += (CEN && !pl.z_fb) ? v : P.srz * v;
+        }
+    }
+    if (T_ON) {
+        T xm[VEC], xp[VEC], wm[VEC], wp[VEC], xm2[VEC], xp2[VEC], fac[VEC];
+        ld_into<T, VEC>(xm, pl.xtm + o);  ld_into<T, VEC>(xp, pl.xtp + o);
+        ld_into<T, VEC>(wm, pl.wtm + o);  ld_into<T, VEC>(wp, pl.wtp + o);
+        if (CEN) { ld_into<T, VEC>(xm2, pl.xtm2 + o); ld_into<T, VEC>(xp2, pl.xtp2 + o); }
+        static_factor<T, VEC>(fac, P, i, j0);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const T v = strip_g_axis<T, SCHEME>(pl.t_fb, pl.at, pl.bt, CEN ? xm2[e] : T(0), xm[e], xr[e + 2], xp[e], CEN ? xp2[e] : T(0), wm[e], wr[e + 1], wp[e]);
+            g[e] += ((CEN && !pl.t_fb) ? v : P.srt * v) * fac[e];
+        }
+    }
+    Pack<T, VEC> pk;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) pk.v[e] = g[e] * (P.inv_div * P.inv_div);
+    st_pack<T, VEC>(g_plane + o, pk);
 }
 
 }  // namespace pytvb

@@ -14,7 +14,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_launches.log 2>&1
 tail -3 $OUT/ncu_launches.log
 echo "== ncu full"
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'cp_(dual|primal)_kernel' -s 6 -c 2 -f -o $OUT/prof_cp \
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:'cp_(dual|primal)_(strip_)?kernel' -s 6 -c 2 -f -o $OUT/prof_cp \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $OUT/ncu_full.log 2>&1
 tail -3 $OUT/ncu_full.log
 ls -la $OUT

@@ -145,6 +145,56 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct EPrimal2 {
     }
 };
 
+template <typename F>
+void for_each_quad_strip(int z_lo, int nz, int M, int Ni, int Nj, int vec, F f) {
+    for (int z = z_lo; z < z_lo + nz; ++z)
+        for (int t = 0; t < M; ++t)
+            for (int i = 0; i < Ni; ++i)
+                for (int j0 = 0; j0 < Nj; j0 += vec) {
+                    const int o = i * Nj + j0;
+                    f(z, t, i, j0, o, i > 0 ? o - Nj : o, i < Ni - 1 ? o + Nj : o);
+                }
+}
+template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct ED2 {
+    static int run(const EArgs<T>& a) {
+        for_each_quad_strip(0, a.P.Nz, a.P.M, a.P.Ni, a.P.Nj, VEC, [&](int z, int t, int i, int j0, int o, int o_up, int o_dn) {
+            const DualPlane<T> pl = make_dual_plane<T, SCHEME>(a.X, a.out, a.P, z, t);
+            strip_quad_D<T, VEC, SCHEME, Z, TT>(pl.y, pl, a.P, i, j0, o, o_up, o_dn);
+        });
+        return 0;
+    }
+};
+template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct EDT2 {
+    static int run(const EArgs<T>& a) {
+        for_each_quad_strip(0, a.P.Nz, a.P.M, a.P.Ni, a.P.Nj, VEC, [&](int z, int t, int i, int j0, int o, int o_up, int o_dn) {
+            const PrimalPlane<T> pl = make_primal_plane<T, SCHEME, Z, TT>(a.F, a.P, z, t);
+            T v[VEC];
+            strip_quad_DT<T, VEC, SCHEME, Z, TT>(v, pl, a.P, i, j0, o, o_up, o_dn);
+            for (int e = 0; e < VEC; ++e) a.out[pl.img + o + e] = v[e];
+        });
+        return 0;
+    }
+};
+template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct ETV2 {
+    static int run(const EArgs<T>& a) {
+        T* Wz0 = const_cast<T*>(a.W.base);
+        double tv = 0;
+        for_each_quad_strip(a.z_lo, a.nz, a.P.M, a.P.Ni, a.P.Nj, VEC, [&](int z, int t, int i, int j0, int o, int o_up, int o_dn) {
+            const DualPlane<T> pl = make_dual_plane<T, SCHEME>(a.X, Wz0, a.P, z, t);
+            const long long img = (long long)z * a.P.sZ + (long long)t * a.P.sT;
+            const bool own = z >= 0 && z < a.P.Nz;
+            const T v = strip_quad_tv_norm<T, VEC, SCHEME, Z, TT>(Wz0 + img, (a.out2 && own) ? a.out2 + img : nullptr, pl, a.P, i, j0, o, o_up, o_dn);
+            if (own) tv += (double)v;
+        });
+        for_each_quad_strip(0, a.P.Nz, a.P.M, a.P.Ni, a.P.Nj, VEC, [&](int z, int t, int i, int j0, int o, int, int) {
+            const GradPlane<T> pl = make_grad_plane<T, SCHEME>(a.X, a.W, a.P, z, t);
+            strip_quad_G<T, VEC, SCHEME, Z, TT>(a.out + (long long)z * a.P.sZ + (long long)t * a.P.sT, pl, a.P, i, j0, o);
+        });
+        *a.sum = tv;
+        return 0;
+    }
+};
+
 template <typename T> int vec_for(const pytvb_problem* pb, int force_scalar) {
     return (force_scalar || pb->Nj % VecOf<T>::value) ? 1 : VecOf<T>::value;
 }
@@ -162,7 +212,10 @@ int run(int op, const pytvb_problem* pb, const void* in, void* out, void* out2, 
     switch (op) {
         case 0: a.X = ImgView<T>{(const T*)in, (const T*)lo, (const T*)hi, 1}; return dispatch<ED, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
         case 1: a.F = FieldView<T>{(const T*)in, (const T*)lo, (const T*)hi}; return dispatch<EDT, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
-        case 2: {
+        case 7: a.X = ImgView<T>{(const T*)in, (const T*)lo, (const T*)hi, 1}; return dispatch<ED2, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
+        case 8: a.F = FieldView<T>{(const T*)in, (const T*)lo, (const T*)hi}; return dispatch<EDT2, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
+        case 2:
+        case 9: {
             const bool has_lo = ax.z_on && pb->z_offset > 0, has_hi = ax.z_on && pb->z_offset + pb->Nz < pb->Nz_global;
             a.X = ImgView<T>{(const T*)in, (const T*)lo, (const T*)hi, 2};
             wbuf.assign((size_t)(a.P.Nz + 2) * a.P.sZ, T(0));
@@ -170,7 +223,7 @@ int run(int op, const pytvb_problem* pb, const void* in, void* out, void* out2, 
             a.W = ImgView<T>{Wz0, wbuf.data(), Wz0 + (long long)a.P.Nz * a.P.sZ, 1};
             a.z_lo = has_lo ? -1 : 0;
             a.nz = a.P.Nz + (has_lo ? 1 : 0) + (has_hi ? 1 : 0);
-            return dispatch<ETV, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
+            return op == 2 ? dispatch<ETV, T>(vec, pb->scheme, ax.z_on, ax.t_on, a) : dispatch<ETV2, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
         }
         case 3: a.X = ImgView<T>{(const T*)in, (const T*)lo, (const T*)hi, 1}; return dispatch<EDual, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
         case 4: a.F = FieldView<T>{(const T*)in, (const T*)lo, (const T*)hi}; return dispatch<EPrimal, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
@@ -183,7 +236,7 @@ int run(int op, const pytvb_problem* pb, const void* in, void* out, void* out2, 
 }  // namespace
 
 // op: 0 D (in=x, out=D) | 1 DT (in=p, out=img) | 2 tv (in=x, out=G, out2=norms|NULL, sum=tv)
-//     5 / 6: generation-2 (strip) code of 3 / 4, same arguments
+//     5 / 6: generation-2 (strip) code of 3 / 4, same arguments;  7 / 8 / 9: generation-2 code of 0 / 1 / 2
 //     3 cp_dual (in=xbar, out=y in place, c0=sigma, c1=1/lam, sum=l21) | 4 cp_primal (in=y, out=x, aux, x0, c0=tau, c1=theta|sigma_A, variant)
 extern "C" int pytvb_emulate(int op, const pytvb_problem* pb, const void* in, void* out, void* out2, void* aux, const void* x0, const void* lo,
                              const void* hi, double c0, double c1, int variant, int force_scalar, double* sum) {

@@ -26,6 +26,7 @@ def build_emul(force=False):
     return EMUL_SO
 
 
+GEN = 1   # 1: tv_core.cuh quad code, 2: strip_core.cuh (module-level switch used by the tests)
 _h = None
 
 
@@ -72,7 +73,7 @@ def D(x, scheme, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_reg
     x = np.ascontiguousarray(x)
     pb, keep = _problem(scheme, x.dtype, x.shape, reg_z_over_reg, reg_time, mask_static, factor_reg_static, z_offset, Nz_global)
     out = np.full((x.shape[0], nd_of(pb)) + x.shape[1:], np.nan, dtype=x.dtype)
-    _call(0, pb, x, out, lo=lo, hi=hi, scalar=scalar)
+    _call(0 if GEN == 1 else 7, pb, x, out, lo=lo, hi=hi, scalar=scalar)
     return out
 
 
@@ -83,7 +84,7 @@ def D_T(p, scheme, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_r
     pb, keep = _problem(scheme, p.dtype, shape, reg_z_over_reg, reg_time, mask_static, factor_reg_static, z_offset, Nz_global)
     assert nd_of(pb) == p.shape[1]
     out = np.full(shape, np.nan, dtype=p.dtype)
-    _call(1, pb, p, out, lo=lo, hi=hi, scalar=scalar)
+    _call(1 if GEN == 1 else 8, pb, p, out, lo=lo, hi=hi, scalar=scalar)
     return out
 
 
@@ -93,11 +94,8 @@ def tv(x, scheme, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_re
     pb, keep = _problem(scheme, x.dtype, x.shape, reg_z_over_reg, reg_time, mask_static, factor_reg_static, z_offset, Nz_global)
     G = np.full(x.shape, np.nan, dtype=x.dtype)
     norms = np.full(x.shape, np.nan, dtype=x.dtype)
-    val = _call(2, pb, x, G, out2=norms, lo=lo, hi=hi, scalar=scalar)
+    val = _call(2 if GEN == 1 else 9, pb, x, G, out2=norms, lo=lo, hi=hi, scalar=scalar)
     return val, G, norms
-
-
-GEN = 1   # 1: tv_core.cuh quad code, 2: strip_core.cuh (module-level switch used by the tests)
 
 
 def cp_dual(xbar, y, scheme, lam, sigma, lo=None, hi=None, z_offset=0, Nz_global=None, scalar=False, **w):

@@ -11,13 +11,22 @@ from oracle import tv_oracle as orc
 SCHEMES = cases.SCHEMES
 
 
+@pytest.fixture(params=[1, 2], ids=["gen1", "gen2"])
+def gen(request):
+    """Both kernel generations (tv_core.cuh quad code, strip_core.cuh strip code)."""
+    old = em.GEN
+    em.GEN = request.param
+    yield request.param
+    em.GEN = old
+
+
 def _tol(dtype):
     return dict(rtol=0, atol=1e-12) if dtype == np.float64 else dict(rtol=0, atol=1e-5)
 
 
 @pytest.mark.parametrize("scalar", [False, True], ids=["vec", "scalar"])
 @pytest.mark.parametrize("case", [pytest.param(c, id=c["key"]) for c in cases.small_cases()])
-def test_operators_match_reference_goldens(case, scalar, golden_small):
+def test_operators_match_reference_goldens(case, scalar, golden_small, gen):
     key, scheme = case["key"], case["scheme"]
     kw = cases.weight_kwargs(case)
     x = cases.make_image(case)
@@ -34,7 +43,7 @@ def test_operators_match_reference_goldens(case, scalar, golden_small):
 
 
 @pytest.mark.parametrize("case", [pytest.param(c, id=c["key"]) for c in cases.small_cases() if c["wname"] in ("default", "ztmask")])
-def test_float32_within_north_star_tolerance(case, golden_small):
+def test_float32_within_north_star_tolerance(case, golden_small, gen):
     key, scheme = case["key"], case["scheme"]
     kw = cases.weight_kwargs(case)
     x = cases.make_image(case, np.float32)
@@ -51,7 +60,7 @@ def test_float32_within_north_star_tolerance(case, golden_small):
 
 @pytest.mark.parametrize("scheme", SCHEMES)
 @pytest.mark.parametrize("split", [(2, 5), (1, 3, 4), (3,)], ids=["3slabs", "4slabs", "2slabs"])
-def test_slabs_with_halos_reproduce_whole_volume(scheme, split):
+def test_slabs_with_halos_reproduce_whole_volume(scheme, split, gen):
     """Nz-slab decomposition: every slab, given its halo planes, reproduces its part of the
     whole-volume result exactly."""
     rs = np.random.RandomState(21)
@@ -89,15 +98,6 @@ def test_slabs_with_halos_reproduce_whole_volume(scheme, split):
         np.testing.assert_allclose(ns, norms[a:b], atol=1e-13)
         tv_sum += tvs
     assert tv_sum == pytest.approx(tv, rel=1e-13)
-
-
-@pytest.fixture(params=[1, 2], ids=["gen1", "gen2"])
-def gen(request):
-    """Both kernel generations of the CP passes (tv_core.cuh quad code, strip_core.cuh strip code)."""
-    old = em.GEN
-    em.GEN = request.param
-    yield request.param
-    em.GEN = old
 
 
 @pytest.mark.parametrize("scheme", SCHEMES)
@@ -203,7 +203,7 @@ def test_cp_slabs(scheme, gen):
     assert 0.5 * fid + 0.1 * l21 == pytest.approx(e_ref, rel=1e-12)
 
 
-def test_central_nz2_intent():
+def test_central_nz2_intent(gen):
     rs = np.random.RandomState(9)
     x = rs.rand(2, 2, 6, 6)
     for kw in (dict(), dict(reg_time=0.5)):
@@ -216,7 +216,7 @@ def test_central_nz2_intent():
         np.testing.assert_allclose(G, Go, atol=1e-12)
 
 
-def test_non_square_images():
+def test_non_square_images(gen):
     """The kernels take Ni and Nj separately (reference: square only, README.md:259)."""
     rs = np.random.RandomState(13)
     x = rs.rand(3, 2, 5, 12)

@@ -39,6 +39,20 @@ def _need_cuda():
     assert "B200" in torch.cuda.get_device_name(0) or True
 
 
+@pytest.fixture(params=["1", "2"], ids=["gen1", "gen2"], autouse=True)
+def gen(request):
+    """Every test runs against both kernel generations (PYTVB_GEN is read by the library at every call):
+    1 = one quad per thread (tv_core.cuh), 2 = strip kernels (strip_core.cuh, the default)."""
+    import os
+    old = os.environ.get("PYTVB_GEN")
+    os.environ["PYTVB_GEN"] = request.param
+    yield request.param
+    if old is None:
+        del os.environ["PYTVB_GEN"]
+    else:
+        os.environ["PYTVB_GEN"] = old
+
+
 # ------------------------------------------------------------------ golden vectors of the reference
 @pytest.mark.parametrize("case", [pytest.param(c, id=c["key"]) for c in cases.small_cases()])
 def test_small_goldens_float64(case, golden_small):
@@ -293,19 +307,6 @@ def test_non_square_and_unaligned_paths():
 
 
 # ------------------------------------------------------------------ Chambolle-Pock
-@pytest.fixture(params=["1", "2"], ids=["gen1", "gen2"])
-def gen(request):
-    """Both kernel generations of the CP passes (PYTVB_GEN is read by the library at every call)."""
-    import os
-    old = os.environ.get("PYTVB_GEN")
-    os.environ["PYTVB_GEN"] = request.param
-    yield request.param
-    if old is None:
-        del os.environ["PYTVB_GEN"]
-    else:
-        os.environ["PYTVB_GEN"] = old
-
-
 @pytest.mark.parametrize("shape", [(3, 2, 5, 8), (2, 3, 6, 4), (1, 1, 7, 12), (5, 1, 4, 8), (1, 4, 3, 4), (2, 2, 1, 4), (3, 3, 2, 8), (4, 2, 33, 260)],
                          ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("scheme", SCHEMES)
@@ -374,12 +375,13 @@ def test_cp_generations_agree_float32():
     torch.manual_seed(4)
     x0 = torch.rand(6, 3, 64, 128, device="cuda")
     res = {}
+    saved = os.environ.get("PYTVB_GEN")
     for g in ("1", "2"):
         os.environ["PYTVB_GEN"] = g
         s = pytv.CPSolver(x0, lam=0.1, scheme="hybrid", variant="rof", reg_time=2 ** -5)
         s.step(20)
         res[g] = (s.x.clone(), s.y.clone(), s.energy())
-    del os.environ["PYTVB_GEN"]
+    os.environ["PYTVB_GEN"] = saved
     assert float((res["1"][0] - res["2"][0]).abs().max()) < 1e-5
     assert float((res["1"][1] - res["2"][1]).abs().max()) < 1e-5
     assert res["1"][2] == pytest.approx(res["2"][2], rel=1e-6)
