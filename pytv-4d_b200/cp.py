@@ -211,8 +211,38 @@ class CPSolver:
         to_next = self.y[-1, self._zf] if scheme != "downwind" else None
         self.halo.exchange(to_prev, to_next, self._fld_lo, self._fld_hi)
 
+    def capture_graph(self, iterations=1):
+        """Capture `iterations` iterations into a CUDA graph; `step(n)` then replays it for every full multiple.
+        For small volumes (a 256x256 image is 6 kernels of a few microseconds each) the iteration is launch-bound
+        and a graph replay removes the per-launch host cost.  Not available for sharded solvers (the halo exchange
+        is issued by NCCL)."""
+        if self.halo is not None:
+            raise RuntimeError("capture_graph is not supported for distributed solvers")
+        self._graph = None
+        torch.cuda.synchronize()
+        state = (self.x.clone(), self.aux.clone(), self.y.clone(), self.scal.clone(), self.iterations)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self.step(1)                      # warm-up outside the capture (lazy module loading)
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.step(iterations)             # recorded, not executed
+        # undo the warm-up iteration
+        self.x.copy_(state[0]); self.aux.copy_(state[1]); self.y.copy_(state[2]); self.scal.copy_(state[3])
+        self.iterations = state[4]
+        self._graph, self._graph_iters = g, int(iterations)
+        return self
+
     def step(self, n=1):
         """Run n iterations; returns self."""
+        g = getattr(self, "_graph", None)
+        if g is not None and not torch.cuda.is_current_stream_capturing():
+            while n >= self._graph_iters:
+                g.replay()
+                self.iterations += self._graph_iters
+                n -= self._graph_iters
         d_l21 = self.scal[0:1] if self.track_energy else None
         d_fid = self.scal[1:2] if self.track_energy else None
         for _ in range(n):
@@ -235,6 +265,71 @@ class CPSolver:
             dst = x_out_host if isinstance(x_out_host, torch.Tensor) else torch.from_numpy(x_out_host)
             dst.copy_(self.x, non_blocking=True)
         return self.energy()
+
+    # ---- pipelined host streaming: PCIe in both directions overlaps the two passes ------------------------
+    def _pipe_init(self):
+        if getattr(self, "_pipe", None) is None:
+            dev = self.x0.device
+            self._pipe = dict(
+                h2d=torch.cuda.Stream(device=dev), d2h=torch.cuda.Stream(device=dev),
+                x0=[self.x0, torch.empty_like(self.x0)],           # double-buffered data term
+                snap=[torch.empty_like(self.x), torch.empty_like(self.x)],   # x snapshots being downloaded
+                scal=[torch.zeros(2, dtype=torch.float64, device=dev) for _ in range(2)],
+                scal_host=[torch.zeros(2, dtype=torch.float64).pin_memory() for _ in range(2)],
+                d2h_done=[None, None], comp_done=[None, None], k=0)
+        return self._pipe
+
+    def step_host_async(self, x0_host, x_out_host=None):
+        """Pipelined form of `step_host`: enqueue upload (copy stream), iteration (current stream) and download
+        (second copy stream) and return a ticket at once; `wait(ticket)` returns the energy of that step once its
+        download has finished.  Successive calls overlap: while step k computes, the data of step k+1 is being
+        uploaded and the image of step k-1 downloaded (PCIe is full duplex), so the steady-state cost per step is
+        max(upload, download, compute) instead of their sum.  At most two tickets may be outstanding (wait for
+        ticket k-1 before issuing step k+1); host buffers must stay untouched until their ticket has been waited for."""
+        p = self._pipe_init()
+        k = p["k"]
+        slot = k % 2
+        cur = torch.cuda.current_stream()
+        src = x0_host if isinstance(x0_host, torch.Tensor) else torch.from_numpy(x0_host)
+        # upload into the data buffer last read by step k-2 (step k-1 is reading the other one)
+        if p["comp_done"][slot] is not None:
+            p["h2d"].wait_event(p["comp_done"][slot])
+        with torch.cuda.stream(p["h2d"]):
+            p["x0"][slot].copy_(src, non_blocking=True)
+            up = torch.cuda.Event()
+            up.record()
+        cur.wait_event(up)
+        self.x0 = p["x0"][slot]
+        self.step(1)
+        if p["d2h_done"][slot] is not None:
+            cur.wait_event(p["d2h_done"][slot])        # snapshot slot: the download of step k-2 has finished
+        p["snap"][slot].copy_(self.x)
+        p["scal"][slot].copy_(self.scal)
+        done = torch.cuda.Event()
+        done.record()
+        p["comp_done"][slot] = done
+        p["d2h"].wait_event(done)
+        with torch.cuda.stream(p["d2h"]):
+            if x_out_host is not None:
+                dst = x_out_host if isinstance(x_out_host, torch.Tensor) else torch.from_numpy(x_out_host)
+                dst.copy_(p["snap"][slot], non_blocking=True)
+            p["scal_host"][slot].copy_(p["scal"][slot], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        p["d2h_done"][slot] = ev
+        p["k"] = k + 1
+        return (k, slot, ev)
+
+    def wait(self, ticket):
+        """Block until the step behind `ticket` has been downloaded; returns its energy (all-reduced when sharded)."""
+        k, slot, ev = ticket
+        ev.synchronize()
+        s = self._pipe["scal_host"][slot].clone()
+        if self.halo is not None:
+            s = s.to(self.x0.device)
+            self.halo.allreduce_sum(s)
+        l21, fid = s.tolist()
+        return 0.5 * fid + self.lam * l21
 
     def energy(self):
         """0.5 |x - x0|^2 + lam L21(D u) of the last iteration over the WHOLE volume (u = the image the dual pass
