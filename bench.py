@@ -222,7 +222,20 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout: keep stdout clean for the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     n_gpus = world
     if args.gpus != world and rank == 0:
         print("bench.py: --gpus %d but WORLD_SIZE=%d; running on %d" % (args.gpus, world, world), file=sys.stderr)
@@ -260,14 +273,12 @@ def run_ours(args):
     barrier()
     start.record()
     for k in range(K):
-        # the solver's step(), spelled out so that the dominant kernel can be bracketed by events on its stream
-        solver._exchange_image_halos()
+        # the solver's step(), spelled out so that the two passes can be bracketed by events on their stream
+        # (sharded: a pass = boundary planes, halo send/recv started, interior planes)
         ev[k][0].record()
-        solver.ops.cp_dual(solver.pb, solver._dual_input(), solver.y, solver.lam, solver.sigma, solver.scal[0:1], solver._img_lo, solver._img_hi, solver.ws)
+        solver._pass_A()
         ev[k][1].record()
-        solver._exchange_field_halos()
-        solver.ops.cp_primal("rof", solver.pb, solver.y, solver.x, solver.aux, solver.x0, solver.tau, solver.theta, solver.scal[1:2], solver._fld_lo,
-                             solver._fld_hi, solver.ws)
+        solver._pass_B()
         ev[k][2].record()
         solver.iterations += 1
         if world > 1:

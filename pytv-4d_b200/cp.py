@@ -84,8 +84,19 @@ class HaloExchange:
         return r if self.group is None else self.dist.get_global_rank(self.group, r)
 
     def exchange(self, to_prev, to_next, from_prev, from_next):
+        """Blocking form of start_exchange + finish."""
+        self.finish(self.start_exchange(to_prev, to_next, from_prev, from_next))
+
+    def finish(self, reqs):
+        """Make the current stream (NCCL) / the host (gloo) wait for an exchange started earlier."""
+        for req in reqs or ():
+            req.wait()
+
+    def start_exchange(self, to_prev, to_next, from_prev, from_next):
         """Send plane `to_prev` to rank-1 and `to_next` to rank+1; receive into `from_prev` / `from_next`.
-        Any of the four may be None (direction not needed by the scheme)."""
+        Any of the four may be None (direction not needed by the scheme).  Returns the outstanding requests: with
+        NCCL the transfers run on NCCL's stream, ordered after everything enqueued so far on the current stream,
+        and overlap whatever is launched next."""
         ops = []
         P2P = self.dist.P2POp
         if self.prev is not None:
@@ -98,9 +109,7 @@ class HaloExchange:
                 ops.append(P2P(self.dist.isend, to_next, self._global(self.next), self.group))
             if from_next is not None:
                 ops.append(P2P(self.dist.irecv, from_next, self._global(self.next), self.group))
-        if ops:
-            for req in self.dist.batch_isend_irecv(ops):
-                req.wait()
+        return self.dist.batch_isend_irecv(ops) if ops else []
 
     def allreduce_sum(self, t):
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
@@ -169,7 +178,12 @@ class CPSolver:
         self.x = self.x0.clone()
         self.aux = self.x0.clone() if variant == "rof" else torch.zeros_like(self.x0)   # xbar | y_f
         self.y = torch.zeros((shape[0], self.Nd) + shape[1:], dtype=dt, device=dev)
-        self.scal = torch.zeros(2, dtype=torch.float64, device=dev)   # [L21(D xbar), |x - x0|^2] of this slab
+        # partial sums of this slab: [0:3] L21(D u) and [3:6] |x - x0|^2, one slot per sub-slab call of a pass
+        self.scal = torch.zeros(6, dtype=torch.float64, device=dev)
+        self.overlap = True        # sharded runs: hide the halo exchange behind the interior planes of each pass
+        self._pending = None       # outstanding exchange of the image halos for the next dual pass
+        self._field_req = None     # outstanding exchange of the field halos for the primal pass
+        self._pb_cache = {}
         self.ws = self.ops.workspace(self.pb, dev)
         self.iterations = 0
         # halo planes
@@ -191,25 +205,97 @@ class CPSolver:
     def _dual_input(self):
         return self.aux if self.variant == "rof" else self.x
 
-    def _exchange_image_halos(self):
-        if self.halo is None or not self.z_on:
-            return
+    # -- halo traffic.  Image halos: my first plane is the previous rank's halo_hi (needed unless downwind), my last
+    # plane the next rank's halo_lo (unless upwind).  Field halos: the neighbour's adjoint reads my backward-type z
+    # slot at its z = Nz (unless upwind) and my forward-type z slot at its z = -1 (unless downwind).
+    def _start_image_exchange(self):
         src = self._dual_input()
-        scheme = self.scheme
-        # my first plane is the neighbour's halo_hi (needed unless downwind); my last plane its halo_lo (unless upwind)
-        to_prev = src[0] if scheme != "downwind" else None
-        to_next = src[-1] if scheme != "upwind" else None
-        self.halo.exchange(to_prev, to_next, self._img_lo, self._img_hi)
+        to_prev = src[0] if self.scheme != "downwind" else None
+        to_next = src[-1] if self.scheme != "upwind" else None
+        return self.halo.start_exchange(to_prev, to_next, self._img_lo, self._img_hi)
 
-    def _exchange_field_halos(self):
-        if self.halo is None or not self.z_on:
+    def _start_field_exchange(self):
+        to_prev = self.y[0, self._zb] if self.scheme != "upwind" else None
+        to_next = self.y[-1, self._zf] if self.scheme != "downwind" else None
+        return self.halo.start_exchange(to_prev, to_next, self._fld_lo, self._fld_hi)
+
+    def _sub_problem(self, a, b):
+        """Problem descriptor of local planes [a, b) (the whole slab, or a boundary / interior part of it)."""
+        key = (a, b)
+        pb = self._pb_cache.get(key)
+        if pb is None:
+            pb = _lib.Problem.from_buffer_copy(self.pb)
+            pb.Nz = b - a
+            pb.z_offset = self.z_offset + a
+            self._pb_cache[key] = pb
+        return pb
+
+    def _dual_range(self, a, b, slot):
+        """Pass A on local planes [a, b); planes just outside come from the slab itself or from the halo buffers."""
+        if b <= a:
             return
-        scheme = self.scheme
-        # the neighbour's adjoint reads my backward-type z slot at its z = Nz (halo_hi, unless upwind) and my
-        # forward-type z slot at its z = -1 (halo_lo, unless downwind)
-        to_prev = self.y[0, self._zb] if scheme != "upwind" else None
-        to_next = self.y[-1, self._zf] if scheme != "downwind" else None
-        self.halo.exchange(to_prev, to_next, self._fld_lo, self._fld_hi)
+        u = self._dual_input()
+        Nz = self.shape[0]
+        lo = u[a - 1] if a > 0 else self._img_lo
+        hi = u[b] if b < Nz else self._img_hi
+        d = self.scal[slot:slot + 1] if self.track_energy else None
+        self.ops.cp_dual(self._sub_problem(a, b), u[a:b], self.y[a:b], self.lam, self.sigma, d, lo, hi, self.ws)
+
+    def _primal_range(self, a, b, slot):
+        if b <= a:
+            return
+        Nz = self.shape[0]
+        lo = self.y[a - 1, self._zf] if a > 0 else self._fld_lo
+        hi = self.y[b, self._zb] if b < Nz else self._fld_hi
+        d = self.scal[3 + slot:4 + slot] if self.track_energy else None
+        c2 = self.theta if self.variant == "rof" else self.sigma_A
+        self.ops.cp_primal(self.variant, self._sub_problem(a, b), self.y[a:b], self.x[a:b], self.aux[a:b], self.x0[a:b], self.tau, c2, d, lo, hi,
+                           self.ws)
+
+    def _split(self):
+        return self.halo is not None and self.z_on and self.overlap and self.shape[0] >= 2
+
+    def _pass_A(self):
+        """Dual pass.  Sharded: boundary planes first, their z-components go to the neighbours while the interior
+        planes are computed."""
+        Nz = self.shape[0]
+        if self.halo is None or not self.z_on:
+            self._dual_range(0, Nz, 0)
+            return
+        if self._pending is None:                      # first iteration (or after a reset): blocking exchange
+            self._pending = self._start_image_exchange()
+        self.halo.finish(self._pending)
+        self._pending = None
+        if self.track_energy:
+            self.scal[0:3].zero_()
+        if not self._split():
+            self._dual_range(0, Nz, 0)
+            self._field_req = self._start_field_exchange()
+            return
+        self._dual_range(0, 1, 0)
+        self._dual_range(Nz - 1, Nz, 1)
+        self._field_req = self._start_field_exchange()
+        self._dual_range(1, Nz - 1, 2)
+
+    def _pass_B(self):
+        """Primal pass.  Sharded: boundary planes first, then the new xbar boundary planes travel while the interior is
+        updated; they are the halos of the next dual pass."""
+        Nz = self.shape[0]
+        if self.halo is None or not self.z_on:
+            self._primal_range(0, Nz, 0)
+            return
+        self.halo.finish(self._field_req)
+        self._field_req = None
+        if self.track_energy:
+            self.scal[3:6].zero_()
+        if not self._split():
+            self._primal_range(0, Nz, 0)
+            self._pending = self._start_image_exchange()
+            return
+        self._primal_range(0, 1, 0)
+        self._primal_range(Nz - 1, Nz, 1)
+        self._pending = self._start_image_exchange()
+        self._primal_range(1, Nz - 1, 2)
 
     def capture_graph(self, iterations=1):
         """Capture `iterations` iterations into a CUDA graph; `step(n)` then replays it for every full multiple.
@@ -243,14 +329,9 @@ class CPSolver:
                 g.replay()
                 self.iterations += self._graph_iters
                 n -= self._graph_iters
-        d_l21 = self.scal[0:1] if self.track_energy else None
-        d_fid = self.scal[1:2] if self.track_energy else None
         for _ in range(n):
-            self._exchange_image_halos()
-            self.ops.cp_dual(self.pb, self._dual_input(), self.y, self.lam, self.sigma, d_l21, self._img_lo, self._img_hi, self.ws)
-            self._exchange_field_halos()
-            c2 = self.theta if self.variant == "rof" else self.sigma_A
-            self.ops.cp_primal(self.variant, self.pb, self.y, self.x, self.aux, self.x0, self.tau, c2, d_fid, self._fld_lo, self._fld_hi, self.ws)
+            self._pass_A()
+            self._pass_B()
             self.iterations += 1
         return self
 
@@ -274,8 +355,8 @@ class CPSolver:
                 h2d=torch.cuda.Stream(device=dev), d2h=torch.cuda.Stream(device=dev),
                 x0=[self.x0, torch.empty_like(self.x0)],           # double-buffered data term
                 snap=[torch.empty_like(self.x), torch.empty_like(self.x)],   # x snapshots being downloaded
-                scal=[torch.zeros(2, dtype=torch.float64, device=dev) for _ in range(2)],
-                scal_host=[torch.zeros(2, dtype=torch.float64).pin_memory() for _ in range(2)],
+                scal=[torch.zeros(6, dtype=torch.float64, device=dev) for _ in range(2)],
+                scal_host=[torch.zeros(6, dtype=torch.float64).pin_memory() for _ in range(2)],
                 d2h_done=[None, None], comp_done=[None, None], k=0)
         return self._pipe
 
@@ -324,7 +405,8 @@ class CPSolver:
         """Block until the step behind `ticket` has been downloaded; returns its energy (all-reduced when sharded)."""
         k, slot, ev = ticket
         ev.synchronize()
-        s = self._pipe["scal_host"][slot].clone()
+        h = self._pipe["scal_host"][slot]
+        s = torch.stack((h[0:3].sum(), h[3:6].sum()))
         if self.halo is not None:
             s = s.to(self.x0.device)
             self.halo.allreduce_sum(s)
@@ -336,7 +418,7 @@ class CPSolver:
         differentiated: README.md:157).  One all-reduce of two doubles when sharded; synchronises."""
         if not self.track_energy:
             raise RuntimeError("energy tracking was disabled")
-        s = self.scal.clone()
+        s = torch.stack((self.scal[0:3].sum(), self.scal[3:6].sum()))
         if self.halo is not None:
             self.halo.allreduce_sum(s)
         l21, fid = s.tolist()

@@ -53,7 +53,7 @@ def _worker(rank, world, port, scheme, variant, Nz, out_dir):
 
 
 @pytest.mark.parametrize("variant", ["rof", "readme"])
-@pytest.mark.parametrize("scheme,world,Nz", [("hybrid", 2, 5), ("upwind", 2, 4), ("downwind", 2, 4), ("central", 2, 6), ("hybrid", 3, 7)])
+@pytest.mark.parametrize("scheme,world,Nz", [("hybrid", 2, 5), ("upwind", 2, 4), ("downwind", 2, 4), ("central", 2, 6), ("hybrid", 3, 7), ("hybrid", 3, 4), ("central", 3, 5)])
 def test_sharded_cp_equals_single_domain(tmp_path, scheme, world, Nz, variant):
     from oracle import tv_oracle as orc
     port = _free_port()
