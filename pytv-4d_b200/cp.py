@@ -18,6 +18,7 @@ of two doubles.  M and N are never split.  With the z axis off the slabs are ind
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -180,7 +181,11 @@ class CPSolver:
         self.y = torch.zeros((shape[0], self.Nd) + shape[1:], dtype=dt, device=dev)
         # partial sums of this slab: [0:3] L21(D u) and [3:6] |x - x0|^2, one slot per sub-slab call of a pass
         self.scal = torch.zeros(6, dtype=torch.float64, device=dev)
-        self.overlap = True        # sharded runs: hide the halo exchange behind the interior planes of each pass
+        # sharded runs: optionally run the boundary planes of each pass first and hide the halo send/recv behind the
+        # interior planes (PYTVB_OVERLAP=1).  Measured on 8 x B200 (profiles/r01j_*): the exchange is ~1 % of an
+        # iteration and the six extra launches of the split cost as much as it hides (10.23 vs 10.20 ms), so the
+        # default is the plain exchange-then-pass schedule.
+        self.overlap = os.environ.get("PYTVB_OVERLAP", "0") == "1"
         self._pending = None       # outstanding exchange of the image halos for the next dual pass
         self._field_req = None     # outstanding exchange of the field halos for the primal pass
         self._pb_cache = {}

@@ -20,7 +20,8 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, scheme, out_dir):
+def _worker(rank, world, port, scheme, out_dir, overlap):
+    os.environ["PYTVB_OVERLAP"] = overlap
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     import pytv_b200
@@ -44,13 +45,14 @@ def _worker(rank, world, port, scheme, out_dir):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("overlap", ["0", "1"], ids=["blocking", "overlap"])
 @pytest.mark.parametrize("scheme", ["hybrid", "central", "upwind"])
-def test_two_gpu_sharded_cp_equals_single_gpu(tmp_path, scheme):
+def test_two_gpu_sharded_cp_equals_single_gpu(tmp_path, scheme, overlap):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import pytv_b200
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), scheme, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), scheme, str(tmp_path), overlap), nprocs=world, join=True)
     x = np.concatenate([np.load(tmp_path / ("x_%d.npy" % r)) for r in range(world)], axis=0)
     g = torch.Generator().manual_seed(3)
     x0 = torch.rand(12, 3, 64, 64, generator=g)
