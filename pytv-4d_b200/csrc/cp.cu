@@ -12,8 +12,8 @@ using namespace pytvb;
 
 namespace {
 
-// Generation 2 (strip kernels) serves every vectorised call; generation 1 remains for the scalar path
-// (row length not divisible by the vector width, unaligned pointers) and can be forced with PYTVB_GEN=1.
+// Generation 2 (strip kernels) is the default for the vector and the scalar path alike; generation 1 (one
+// quad per thread, exact IEEE division / sqrt) is kept as a cross-check and is selected with PYTVB_GEN=1.
 bool use_gen2() {
     const char* e = getenv("PYTVB_GEN");
     return !e || atoi(e) >= 2;
@@ -22,7 +22,7 @@ bool use_gen2() {
 template <typename T> struct DualArgs { ImgView<T> Xb; T* y; double* partial; Params<T> P; T sigma, inv_lam, lam; cudaStream_t st; long long* nb; };
 template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchDual {
     static int run(const DualArgs<T>& a) {
-        if constexpr (VEC > 1) {
+        {
             if (use_gen2()) {
                 constexpr int R = PYTVB_STRIP_R;
                 const Tiling tl = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.P.Nz, VEC);
@@ -50,7 +50,7 @@ template <typename T> struct PrimalArgs {
 };
 template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchPrimal {
     static int run(const PrimalArgs<T>& a) {
-        if constexpr (VEC > 1) {
+        {
             if (use_gen2()) {
                 constexpr int R = PYTVB_STRIP_R;
                 const Tiling tl = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.P.Nz, VEC);

@@ -135,7 +135,7 @@ inline int check_grid(const Tiling& tl) {
 // Workspace layout for reductions: [partials: max CTAs][stage 2: 256 doubles]
 constexpr int REDUCE_STAGE2 = 256;
 inline long long max_partials(const pytvb_problem* pb) {
-    // worst case: scalar path, one extra halo plane on each side (tv sweep 1)
+    // worst case: generation-1 scalar path (one thread per voxel), one extra halo plane on each side (tv sweep 1)
     const Tiling tl = make_tiling((int)pb->Nj, (int)pb->Ni, (int)pb->M, 0, (int)pb->Nz + 2, 1);
     return tl.nblocks;
 }

@@ -20,7 +20,7 @@ bool use_gen2() {
 template <typename T> struct DArgs { ImgView<T> X; T* D; Params<T> P; int vec; cudaStream_t st; };
 template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchD {
     static int run(const DArgs<T>& a) {
-        if constexpr (VEC > 1) {
+        {
             if (use_gen2()) {
                 constexpr int R = PYTVB_STRIP_R;
                 const Tiling tl = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.P.Nz, VEC);
@@ -43,7 +43,7 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchD {
 template <typename T> struct DTArgs { FieldView<T> F; T* out; Params<T> P; cudaStream_t st; };
 template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchDT {
     static int run(const DTArgs<T>& a) {
-        if constexpr (VEC > 1) {
+        {
             if (use_gen2()) {
                 constexpr int R = PYTVB_STRIP_R;
                 const Tiling tl = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.P.Nz, VEC);
@@ -93,11 +93,14 @@ int run_l21(const pytvb_problem* pb, const void* D, int Nd, void* norms, double*
     P.sZf = P.sC * Nd;
     const int vec = pick_vec<T>(pb, {D, norms});
     double* partial = (double*)ws;
-    if (vec > 1 && use_gen2()) {
+    if (use_gen2()) {
         constexpr int R = PYTVB_STRIP_R;
         const Tiling tl = make_strip_tiling<R>(P.Nj, P.Ni, P.M, P.Nz, vec);
         if (int rc = check_grid(tl)) return rc;
-        l21_strip_kernel<T, VecOf<T>::value, R><<<(unsigned)tl.nblocks, CTA_THREADS, 0, st>>>((const T*)D, Nd, (T*)norms, partial, P, tl);
+        if (vec > 1)
+            l21_strip_kernel<T, VecOf<T>::value, R><<<(unsigned)tl.nblocks, CTA_THREADS, 0, st>>>((const T*)D, Nd, (T*)norms, partial, P, tl);
+        else
+            l21_strip_kernel<T, 1, R><<<(unsigned)tl.nblocks, CTA_THREADS, 0, st>>>((const T*)D, Nd, (T*)norms, partial, P, tl);
         count_launches(1);
         PYTVB_CUDA(cudaGetLastError());
         return finalize_sum(partial, tl.nblocks, d_sum, st);

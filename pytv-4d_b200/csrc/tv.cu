@@ -24,7 +24,7 @@ template <typename T> struct TvArgs {
 
 template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchTv {
     static int run(const TvArgs<T>& a) {
-        if constexpr (VEC > 1) {
+        {
             if (use_gen2()) {
                 constexpr int R = PYTVB_STRIP_R;
                 const Tiling t1 = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.nz, VEC, a.z_lo);
