@@ -67,6 +67,14 @@ class CudaOps:
     def workspace(self, pb, device):
         return _dev.reduce_workspace(pb, device)
 
+    def fused_workspace(self, pb, device):
+        return torch.empty(self.lib.pytvb_fused_workspace_bytes(ctypes.byref(pb)), dtype=torch.uint8, device=device)
+
+    def cp_iter_fused(self, variant, pb, u, y, x, aux, x0, lam, sigma, tau, c2, d_l21, d_fid, ws):
+        _lib.check(self.lib.pytvb_cp_iter_fused(ctypes.byref(pb), 0 if variant == "rof" else 1, _dev.ptr(u), _dev.ptr(y), _dev.ptr(x), _dev.ptr(aux),
+                                                _dev.ptr(x0), lam, sigma, tau, c2, _dev.ptr(d_l21), _dev.ptr(d_fid), None, None, None, None,
+                                                _dev.ptr(ws), _dev.stream_ptr()))
+
 
 class HaloExchange:
     """Nearest-neighbour plane exchange between z-slabs over torch.distributed (NCCL send/recv on NVLink;
@@ -127,7 +135,7 @@ class CPSolver:
 
     def __init__(self, x0, lam, scheme="hybrid", variant="rof", sigma=0.5, tau=None, theta=1.0, sigma_A=1.0, reg_z_over_reg=1.0,
                  reg_time=0.0, mask_static=False, factor_reg_static=0, distributed=False, group=None, z_offset=None, Nz_global=None,
-                 ops=None, track_energy=True):
+                 ops=None, track_energy=True, fused=None):
         if scheme not in _dev.SCHEMES:
             raise ValueError("unknown scheme %r" % (scheme,))
         if variant not in ("rof", "readme"):
@@ -190,6 +198,12 @@ class CPSolver:
         self._field_req = None     # outstanding exchange of the field halos for the primal pass
         self._pb_cache = {}
         self.ws = self.ops.workspace(self.pb, dev)
+        # single-launch iteration (generation 3): pass B follows pass A a few planes behind inside one kernel and
+        # reads y from L2.  Whole volumes on one GPU only; PYTVB_FUSED=1 or fused=True selects it.
+        if fused is None:
+            fused = os.environ.get("PYTVB_FUSED", "0") == "1"
+        self.fused = bool(fused) and self.halo is None and hasattr(self.ops, "cp_iter_fused")
+        self._fused_ws = self.ops.fused_workspace(self.pb, dev) if self.fused else None
         self.iterations = 0
         # halo planes
         self._img_lo = self._img_hi = self._fld_lo = self._fld_hi = None
@@ -335,8 +349,13 @@ class CPSolver:
                 self.iterations += self._graph_iters
                 n -= self._graph_iters
         for _ in range(n):
-            self._pass_A()
-            self._pass_B()
+            if self.fused:
+                c2 = self.theta if self.variant == "rof" else self.sigma_A
+                self.ops.cp_iter_fused(self.variant, self.pb, self._dual_input(), self.y, self.x, self.aux, self.x0, self.lam, self.sigma, self.tau, c2,
+                                       self.scal[0:1] if self.track_energy else None, self.scal[3:4] if self.track_energy else None, self._fused_ws)
+            else:
+                self._pass_A()
+                self._pass_B()
             self.iterations += 1
         return self
 

@@ -140,19 +140,21 @@ inline long long max_partials(const pytvb_problem* pb) {
     return tl.nblocks;
 }
 
-// partials[0..n) -> d_out[0]; fixed summation order.
-inline int finalize_sum(double* partials, long long n, double* d_out, cudaStream_t st) {
+// partials[0..n) -> d_out[0]; fixed summation order.  stage2: REDUCE_STAGE2 doubles of scratch.
+inline int finalize_sum_at(double* partials, long long n, double* stage2, double* d_out, cudaStream_t st) {
     if (n <= 8192) {
         reduce_chunks_kernel<<<1, CTA_THREADS, 0, st>>>(partials, n, d_out, 1.0);
         count_launches(1);
     } else {
-        double* stage2 = partials + n;
         reduce_chunks_kernel<<<REDUCE_STAGE2, CTA_THREADS, 0, st>>>(partials, n, stage2, 1.0);
         reduce_chunks_kernel<<<1, CTA_THREADS, 0, st>>>(stage2, REDUCE_STAGE2, d_out, 1.0);
         count_launches(2);
     }
     PYTVB_CUDA(cudaGetLastError());
     return PYTVB_OK;
+}
+inline int finalize_sum(double* partials, long long n, double* d_out, cudaStream_t st) {
+    return finalize_sum_at(partials, n, partials + n, d_out, st);
 }
 
 }  // namespace pytvb

@@ -260,8 +260,32 @@ PYTVB_HD void adj_operands(T& m, T& p, T f_m, T f_c, T b_c, T b_p, bool fallback
     else { m = f_m; p = b_p; }
 }
 
+// Loads of the dual field in the adjoint.  CG = true (generation 3 only, device only): ld.global.cg, because the
+// field was rewritten by other CTAs of the SAME launch and this SM's L1 may hold pre-update lines.
+template <typename T, int VEC> struct CgLoad;
+#if defined(__CUDACC__)
+template <> struct CgLoad<float, 4> { static __device__ __forceinline__ void ld(float* d, const float* p) { const float4 v = __ldcg(reinterpret_cast<const float4*>(p)); d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; } };
+template <> struct CgLoad<float, 1> { static __device__ __forceinline__ void ld(float* d, const float* p) { d[0] = __ldcg(p); } };
+template <> struct CgLoad<double, 2> { static __device__ __forceinline__ void ld(double* d, const double* p) { const double2 v = __ldcg(reinterpret_cast<const double2*>(p)); d[0] = v.x; d[1] = v.y; } };
+template <> struct CgLoad<double, 1> { static __device__ __forceinline__ void ld(double* d, const double* p) { d[0] = __ldcg(p); } };
+#endif
+template <typename T, int VEC, bool CG>
+PYTVB_HD void ld_field(T* dst, const T* src) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (CG) { CgLoad<T, VEC>::ld(dst, src); return; }
+#endif
+    ld_into<T, VEC>(dst, src);
+}
+template <typename T, bool CG>
+PYTVB_HD T ld_field1(const T* src) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (CG) { T v; CgLoad<T, 1>::ld(&v, src); return v; }
+#endif
+    return *src;
+}
+
 // D^T y at one quad (times inv_div), strip addressing.
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON>
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, bool CG = false>
 PYTVB_HD void strip_quad_DT(T* out, const PrimalPlane<T>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn) {
     typedef Comp<SCHEME, Z_ON, T_ON> C;
     constexpr bool NF = (SCHEME != DOWNWIND);   // reads the forward-type slot at k-1 (centred: C[k-1])
@@ -276,10 +300,10 @@ PYTVB_HD void strip_quad_DT(T* out, const PrimalPlane<T>& pl, const Params<T>& P
     {
         T a, b, f_m[VEC], f_c[VEC], b_c[VEC], b_p[VEC];
         adj_factors<T, SCHEME>(a, b, i, P.Ni, false);
-        if (NF) ld_into<T, VEC>(f_m, yI_F + o_up); else zero_into<T, VEC>(f_m);
-        if (!CTR && NF) ld_into<T, VEC>(f_c, yI_F + o); else zero_into<T, VEC>(f_c);
-        if (!CTR && NB) ld_into<T, VEC>(b_c, yI_B + o); else zero_into<T, VEC>(b_c);
-        if (NB) ld_into<T, VEC>(b_p, yI_B + o_dn); else zero_into<T, VEC>(b_p);
+        if (NF) ld_field<T, VEC, CG>(f_m, yI_F + o_up); else zero_into<T, VEC>(f_m);
+        if (!CTR && NF) ld_field<T, VEC, CG>(f_c, yI_F + o); else zero_into<T, VEC>(f_c);
+        if (!CTR && NB) ld_field<T, VEC, CG>(b_c, yI_B + o); else zero_into<T, VEC>(b_c);
+        if (NB) ld_field<T, VEC, CG>(b_p, yI_B + o_dn); else zero_into<T, VEC>(b_p);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
             T m, p;
@@ -292,16 +316,16 @@ PYTVB_HD void strip_quad_DT(T* out, const PrimalPlane<T>& pl, const Params<T>& P
         T f[VEC + 2], bq[VEC + 2];
 #pragma unroll
         for (int e = 0; e < VEC + 2; ++e) bq[e] = T(0);
-        ld_into<T, VEC>(f + 1, yJ_F + o);
-        f[0] = (NF && j0 > 0) ? yJ_F[o - 1] : T(0);
-        f[VEC + 1] = (CTR && j0 + VEC < P.Nj) ? yJ_F[o + VEC] : T(0);
+        ld_field<T, VEC, CG>(f + 1, yJ_F + o);
+        f[0] = (NF && j0 > 0) ? ld_field1<T, CG>(yJ_F + o - 1) : T(0);
+        f[VEC + 1] = (CTR && j0 + VEC < P.Nj) ? ld_field1<T, CG>(yJ_F + o + VEC) : T(0);
         if (SCHEME == HYBRID || SCHEME == DOWNWIND) {
-            if (SCHEME == HYBRID) ld_into<T, VEC>(bq + 1, yJ_B + o);
+            if (SCHEME == HYBRID) ld_field<T, VEC, CG>(bq + 1, yJ_B + o);
             else {
 #pragma unroll
                 for (int e = 0; e < VEC + 2; ++e) bq[e] = f[e];
             }
-            bq[VEC + 1] = (j0 + VEC < P.Nj) ? yJ_B[o + VEC] : T(0);
+            bq[VEC + 1] = (j0 + VEC < P.Nj) ? ld_field1<T, CG>(yJ_B + o + VEC) : T(0);
         }
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
@@ -317,10 +341,10 @@ PYTVB_HD void strip_quad_DT(T* out, const PrimalPlane<T>& pl, const Params<T>& P
         const bool fb = P.z_fwd_fallback != 0;
         const bool up_form = !CTR || fb;   // needs the slot at k itself
         T f_m[VEC], f_c[VEC], b_c[VEC], b_p[VEC];
-        if (NF) ld_into<T, VEC>(f_m, pl.zf_m + o); else zero_into<T, VEC>(f_m);
-        if (up_form && NF) ld_into<T, VEC>(f_c, pl.y + (long long)C::Z_F * P.sC + o); else zero_into<T, VEC>(f_c);
-        if (!CTR && NB) ld_into<T, VEC>(b_c, pl.y + (long long)C::Z_B * P.sC + o); else zero_into<T, VEC>(b_c);
-        if (NB && !(CTR && fb)) ld_into<T, VEC>(b_p, pl.zb_p + o); else zero_into<T, VEC>(b_p);
+        if (NF) ld_field<T, VEC, CG>(f_m, pl.zf_m + o); else zero_into<T, VEC>(f_m);
+        if (up_form && NF) ld_field<T, VEC, CG>(f_c, pl.y + (long long)C::Z_F * P.sC + o); else zero_into<T, VEC>(f_c);
+        if (!CTR && NB) ld_field<T, VEC, CG>(b_c, pl.y + (long long)C::Z_B * P.sC + o); else zero_into<T, VEC>(b_c);
+        if (NB && !(CTR && fb)) ld_field<T, VEC, CG>(b_p, pl.zb_p + o); else zero_into<T, VEC>(b_p);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
             T m, p;
@@ -332,10 +356,10 @@ PYTVB_HD void strip_quad_DT(T* out, const PrimalPlane<T>& pl, const Params<T>& P
         const bool fb = P.t_fwd_fallback != 0;
         const bool up_form = !CTR || fb;
         T f_m[VEC], f_c[VEC], b_c[VEC], b_p[VEC], fac[VEC];
-        if (NF) ld_into<T, VEC>(f_m, pl.tf_m + o); else zero_into<T, VEC>(f_m);
-        if (up_form && NF) ld_into<T, VEC>(f_c, pl.y + (long long)C::T_F * P.sC + o); else zero_into<T, VEC>(f_c);
-        if (!CTR && NB) ld_into<T, VEC>(b_c, pl.y + (long long)C::T_B * P.sC + o); else zero_into<T, VEC>(b_c);
-        if (NB && !(CTR && fb)) ld_into<T, VEC>(b_p, pl.tb_p + o); else zero_into<T, VEC>(b_p);
+        if (NF) ld_field<T, VEC, CG>(f_m, pl.tf_m + o); else zero_into<T, VEC>(f_m);
+        if (up_form && NF) ld_field<T, VEC, CG>(f_c, pl.y + (long long)C::T_F * P.sC + o); else zero_into<T, VEC>(f_c);
+        if (!CTR && NB) ld_field<T, VEC, CG>(b_c, pl.y + (long long)C::T_B * P.sC + o); else zero_into<T, VEC>(b_c);
+        if (NB && !(CTR && fb)) ld_field<T, VEC, CG>(b_p, pl.tb_p + o); else zero_into<T, VEC>(b_p);
         static_factor<T, VEC>(fac, P, i, j0);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
@@ -350,11 +374,11 @@ PYTVB_HD void strip_quad_DT(T* out, const PrimalPlane<T>& pl, const Params<T>& P
 
 // Primal update at one quad.  VARIANT 0: ROF prox + over-relaxation (aux = xbar); 1: README form (aux = y_f).
 // c1 = 1/(1+tau) (rof) or 1/(1+sigma_A) (readme); c2 = theta or sigma_A.  Returns sum (x_new - x0)^2.
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int VARIANT>
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int VARIANT, bool CG = false>
 PYTVB_HD T strip_quad_cp_primal(T* x, T* aux, const T* x0, const PrimalPlane<T>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn,
                                 T tau, T c1, T c2) {
     T dty[VEC];
-    strip_quad_DT<T, VEC, SCHEME, Z_ON, T_ON>(dty, pl, P, i, j0, o, o_up, o_dn);
+    strip_quad_DT<T, VEC, SCHEME, Z_ON, T_ON, CG>(dty, pl, P, i, j0, o, o_up, o_dn);
     const long long off = pl.img + o;
     const Pack<T, VEC> xo = ld_pack<T, VEC>(x + off), x0q = ld_pack<T, VEC>(x0 + off);
     Pack<T, VEC> xn, ax;

@@ -368,6 +368,32 @@ def test_cp_small4d_golden(scheme, dtype, golden_kat, gen):
     assert x[1, 1, 3, 4] == pytest.approx(g["rof_x_probe"], rel=1e-11 if dtype == np.float64 else 1e-4)
 
 
+@pytest.mark.parametrize("lag", ["1", "3"])
+@pytest.mark.parametrize("shape", [(6, 2, 70, 8), (3, 3, 130, 12), (1, 1, 65, 4), (5, 1, 3, 8), (9, 2, 67, 1028), (12, 4, 256, 256)],
+                         ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_fused_single_launch_iteration(scheme, shape, lag):
+    """Generation 3 (pass B lagging pass A inside one launch) is bitwise equal to the two-pass iteration, for both
+    forms, over several iterations (float32 and float64)."""
+    import os
+    os.environ["PYTVB_FUSED_LAG"] = lag
+    os.environ["PYTVB_GEN"] = "2"          # the single-launch kernel shares its per-quad code with generation 2
+    torch.manual_seed(41)
+    for dtype in (torch.float32, torch.float64):
+        x0 = torch.rand(shape, dtype=dtype, device="cuda")
+        for variant in ("rof", "readme"):
+            kw = dict(lam=0.1, scheme=scheme, variant=variant, reg_z_over_reg=0.6, reg_time=0.4)
+            a = pytv.CPSolver(x0, fused=False, **kw)
+            b = pytv.CPSolver(x0, fused=True, **kw)
+            assert b.fused
+            for _ in range(4):
+                a.step(); b.step()
+                # per-thread partial sums group different rows (pass B tiles sit one row higher): float rounding only
+                assert a.energy() == pytest.approx(b.energy(), rel=1e-6 if dtype == torch.float32 else 1e-12)
+            assert torch.equal(a.x, b.x) and torch.equal(a.y, b.y) and torch.equal(a.aux, b.aux)
+    del os.environ["PYTVB_FUSED_LAG"]
+
+
 def test_cp_generations_agree_float32():
     """gen-1 (exact sqrt / division) and gen-2 (rsqrt, reciprocal) float32 kernels stay within 1e-6 of each other
     over 20 iterations on a 4-D volume large enough for many CTAs."""
