@@ -88,6 +88,10 @@ int pytvb_apply_mask(const pytvb_problem* pb, void* x, const uint8_t* mask, int 
 int pytvb_tv(const pytvb_problem* pb, const void* x, void* G, void* norms_or_null, double* d_tv, const void* halo_lo2,
              const void* halo_hi2, void* ws_reduce, void* ws_tv, void* stream);
 
+/* TV value only, d_tv[0] = L21(D_<scheme>(x)) without materialising D or the sub-gradient (one read of x):
+ * the TV term of a primal energy / duality gap.  halos: as pytvb_D (ONE image plane each side). */
+int pytvb_tv_value(const pytvb_problem* pb, const void* x, double* d_tv, const void* halo_lo, const void* halo_hi, void* ws, void* stream);
+
 /* Fused Chambolle-Pock iteration = pass A + pass B (reference: user loop README.md:145-157).
  * Pass A (dual):    y <- proj_{|.|_2 <= lam}( y + sigma * D(xbar) )           [README.md:149-151]
  *                   d_l21_or_null[0] = L21(D(xbar))  (the TV term of the loss, README.md:157)

@@ -55,6 +55,7 @@ _PROTOTYPES = {
     "pytvb_l21": (ctypes.c_int, [_PB, _VP, ctypes.c_int64, _VP, _VP, _VP, _VP]),
     "pytvb_apply_mask": (ctypes.c_int, [_PB, _VP, _VP, ctypes.c_int, _VP]),
     "pytvb_tv": (ctypes.c_int, [_PB, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "pytvb_tv_value": (ctypes.c_int, [_PB, _VP, _VP, _VP, _VP, _VP, _VP]),
     "pytvb_cp_dual": (ctypes.c_int, [_PB, _VP, _VP, ctypes.c_double, ctypes.c_double, _VP, _VP, _VP, _VP, _VP]),
     "pytvb_cp_primal_rof": (ctypes.c_int, [_PB, _VP, _VP, _VP, _VP, ctypes.c_double, ctypes.c_double, _VP, _VP, _VP, _VP, _VP]),
     "pytvb_cp_primal_readme": (ctypes.c_int, [_PB, _VP, _VP, _VP, _VP, ctypes.c_double, ctypes.c_double, _VP, _VP, _VP, _VP, _VP]),

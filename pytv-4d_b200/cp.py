@@ -67,6 +67,12 @@ class CudaOps:
     def workspace(self, pb, device):
         return _dev.reduce_workspace(pb, device)
 
+    def tv_value(self, pb, x, d_tv, lo, hi, ws):
+        _lib.check(self.lib.pytvb_tv_value(ctypes.byref(pb), _dev.ptr(x), _dev.ptr(d_tv), _dev.ptr(lo), _dev.ptr(hi), _dev.ptr(ws), _dev.stream_ptr()))
+
+    def adjoint(self, pb, y, out, lo, hi):
+        _lib.check(self.lib.pytvb_DT(ctypes.byref(pb), _dev.ptr(y), _dev.ptr(out), _dev.ptr(lo), _dev.ptr(hi), _dev.stream_ptr()))
+
     def fused_workspace(self, pb, device):
         return torch.empty(self.lib.pytvb_fused_workspace_bytes(ctypes.byref(pb)), dtype=torch.uint8, device=device)
 
@@ -448,8 +454,146 @@ class CPSolver:
         l21, fid = s.tolist()
         return 0.5 * fid + self.lam * l21
 
+    # ---- primal-dual gap, stopping rule, data-term hook ----------------------------
+    def _sync_halos_for_diagnostics(self):
+        """The halo buffers are about to be reused: retire the exchange that was prefetched for the next pass A."""
+        if self.halo is not None and self._pending is not None:
+            self.halo.finish(self._pending)
+            self._pending = None
+
+    def primal_energy(self):
+        """P(x) = 0.5 |x - x0|^2 + lam TV(x) at the current iterate, over the whole volume (synchronises)."""
+        lo = hi = None
+        if self.halo is not None and self.z_on:
+            self._sync_halos_for_diagnostics()
+            to_prev = self.x[0] if self.scheme != "downwind" else None
+            to_next = self.x[-1] if self.scheme != "upwind" else None
+            self.halo.exchange(to_prev, to_next, self._img_lo, self._img_hi)
+            lo, hi = self._img_lo, self._img_hi
+        d = torch.zeros(2, dtype=torch.float64, device=self.x.device)
+        self.ops.tv_value(self.pb, self.x, d[0:1], lo, hi, self.ws)
+        d[1] = torch.sum((self.x - self.x0).double() ** 2) if self.x.numel() < (1 << 28) else sum(
+            torch.sum((self.x[k] - self.x0[k]).double() ** 2) for k in range(self.shape[0]))
+        if self.halo is not None:
+            self.halo.allreduce_sum(d)
+        tv, fid = d.tolist()
+        return 0.5 * fid + self.lam * tv
+
+    def dual_energy(self):
+        """D(y) = 0.5 |x0|^2 - 0.5 |x0 - D^T y|^2 for the feasible dual iterate y (|y_v|_2 <= lam after the projection)."""
+        lo = hi = None
+        if self.halo is not None and self.z_on:
+            to_prev = self.y[0, self._zb] if self.scheme != "upwind" else None
+            to_next = self.y[-1, self._zf] if self.scheme != "downwind" else None
+            self.halo.exchange(to_prev, to_next, self._fld_lo, self._fld_hi)
+            lo, hi = self._fld_lo, self._fld_hi
+        dty = torch.empty_like(self.x)
+        self.ops.adjoint(self.pb, self.y, dty, lo, hi)
+        d = torch.zeros(2, dtype=torch.float64, device=self.x.device)
+        for k in range(self.shape[0]):          # plane by plane: no volume-sized float64 temporaries
+            x0k = self.x0[k].double()
+            d[0] += torch.sum(x0k * x0k)
+            d[1] += torch.sum((x0k - dty[k].double()) ** 2)
+        if self.halo is not None:
+            self.halo.allreduce_sum(d)
+        a, b = d.tolist()
+        return 0.5 * a - 0.5 * b
+
+    def gap(self):
+        """(primal, dual, primal - dual); the gap is >= 0 and vanishes at the solution of the ROF problem."""
+        p, d = self.primal_energy(), self.dual_energy()
+        return p, d, p - d
+
+    def solve(self, max_iter=1000, tol=1e-4, check_every=25, callback=None):
+        """Iterate until the relative primal-dual gap (P - D) / max(|P|, tiny) <= tol or max_iter is reached.
+        Returns a dict with the number of iterations and the final energies.  `callback(solver, it, P, D)` is called
+        at every check (e.g. to record a convergence curve)."""
+        info = dict(iterations=0, converged=False)
+        it = 0
+        while it < max_iter:
+            n = min(check_every, max_iter - it)
+            self.step(n)
+            it += n
+            p, d, g = self.gap()
+            if callback is not None:
+                callback(self, it, p, d)
+            info.update(iterations=it, primal=p, dual=d, gap=g, relative_gap=g / max(abs(p), 1e-300))
+            if g <= tol * max(abs(p), 1e-300):
+                info["converged"] = True
+                break
+        return info
+
+    def set_data(self, x0, reset_primal=False, reset_dual=False):
+        """Data-term hook: replace the data x0 of 0.5|x - x0|^2 (e.g. the gradient step of an outer reconstruction loop,
+        x0 = x - t A^T(Ax - b)); the dual variable is kept as a warm start unless reset_dual."""
+        src = x0 if isinstance(x0, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(x0))
+        self.x0.copy_(src.to(self.x0.dtype), non_blocking=True)
+        if reset_primal:
+            self.x.copy_(self.x0)
+            if self.variant == "rof":
+                self.aux.copy_(self.x0)
+            self._pending = None
+        if reset_dual:
+            self.y.zero_()
+        return self
+
     def result(self, return_pytorch_tensor=False):
         return self.x if return_pytorch_tensor else self.x.detach().cpu().numpy()
+
+
+class TVProx:
+    """prox_{lam TV}(v) = argmin_x 0.5|x - v|^2 + lam TV(x) as a reusable operator for outer algorithms (proximal
+    gradient / ADMM reconstructions, README.md:3): the dual variable is warm-started from the previous call."""
+
+    def __init__(self, example, lam, scheme="hybrid", n_iter=20, **weights):
+        self.solver = CPSolver(example, lam, scheme=scheme, variant="rof", track_energy=False, **weights)
+        self.n_iter = int(n_iter)
+
+    def __call__(self, v, lam=None, n_iter=None):
+        if lam is not None:
+            self.solver.lam = float(lam)
+        self.solver.set_data(v, reset_primal=True)
+        self.solver.step(self.n_iter if n_iter is None else int(n_iter))
+        return self.solver.x
+
+
+def denoise_tv_chambolle(image, weight=0.1, eps=2e-4, max_num_iter=200, channel_axis=None):
+    """Same call as skimage.restoration.denoise_tv_chambolle (the reference's TODO, README.md:260): isotropic TV with
+    forward differences (the upwind scheme), objective 0.5|x - image|^2 + weight TV(x), stopped when the energy changes
+    by less than eps times its initial value.  2-D or 3-D images; channels (channel_axis) are denoised independently."""
+    img = np.asarray(image) if not isinstance(image, torch.Tensor) else image
+    was_tensor = isinstance(img, torch.Tensor)
+    arr = img if was_tensor else torch.as_tensor(np.ascontiguousarray(img))
+    if channel_axis is not None:
+        arr = arr.movedim(channel_axis, 0)
+        spatial = arr.shape[1:]
+        vol = arr.reshape((arr.shape[0],) + tuple(spatial))
+        vol = vol[None] if len(spatial) == 2 else vol.movedim(0, 1)        # (1, C, H, W) or (D, C, H, W): channels on the M axis
+    else:
+        spatial = arr.shape
+        vol = arr.reshape((1, 1) + tuple(spatial)) if len(spatial) == 2 else arr.reshape((spatial[0], 1) + tuple(spatial[1:]))
+    if len(spatial) not in (2, 3):
+        raise ValueError("denoise_tv_chambolle handles 2-D and 3-D images")
+    vol = vol.contiguous()
+    if vol.dtype not in (torch.float32, torch.float64):
+        vol = vol.to(torch.float64)
+    solver = CPSolver(vol, weight, scheme="upwind", variant="rof", reg_z_over_reg=1.0, reg_time=0.0)
+    e_prev = e_init = None
+    for it in range(int(max_num_iter)):
+        solver.step(1)
+        e = solver.energy()
+        if it == 0:
+            e_init = e
+        elif abs(e_prev - e) < eps * e_init:
+            break
+        e_prev = e
+    out = solver.x
+    if channel_axis is not None:
+        out = out[0] if len(spatial) == 2 else out.movedim(1, 0)
+        out = out.movedim(0, channel_axis)
+    else:
+        out = out.reshape(tuple(spatial))
+    return out if was_tensor else out.cpu().numpy()
 
 
 def cp_denoise(x0, lam, n_iter, scheme="hybrid", variant="rof", return_pytorch_tensor=False, return_energy=False, **kw):

@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(CTA_THREADS) tv_norm_strip_kernel(ImgView<T> X
         const bool own = q.z >= 0 && q.z < P.Nz;
         T* np = (norms && own) ? norms + img : nullptr;
         for_strip_rows<R>(q, P.Ni, P.Nj, [&](int i, int o, int o_up, int o_dn) {
-            const T v = strip_quad_tv_norm<T, VEC, SCHEME, Z_ON, T_ON>(Wz0 + img, np, pl, P, i, q.j0, o, o_up, o_dn);
+            const T v = strip_quad_tv_norm<T, VEC, SCHEME, Z_ON, T_ON>(Wz0 ? Wz0 + img : nullptr, np, pl, P, i, q.j0, o, o_up, o_dn);
             if (own) sum += v;
         });
     }

@@ -190,7 +190,7 @@ PYTVB_HD T strip_quad_tv_norm(T* w_plane, T* n_plane, const DualPlane<T>& pl, co
         n.v[e] = s > T(0) ? nr : T(INFINITY);
         sum += nr;
     }
-    st_pack<T, VEC>(w_plane + o, w);
+    if (w_plane) st_pack<T, VEC>(w_plane + o, w);
     if (n_plane) st_pack<T, VEC>(n_plane + o, n);
     return sum;
 }

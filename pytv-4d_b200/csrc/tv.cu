@@ -83,6 +83,45 @@ int run_tv(const pytvb_problem* pb, const void* x, void* G, void* norms, double*
 
 }  // namespace
 
+namespace {
+// TV value only: sweep 1 without the inverse-norm output (primal energy / duality gap evaluations).
+template <typename T> struct TvValArgs { ImgView<T> X; double* partial; Params<T> P; cudaStream_t st; long long* nb; };
+template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchTvVal {
+    static int run(const TvValArgs<T>& a) {
+        constexpr int R = PYTVB_STRIP_R;
+        const Tiling tl = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.P.Nz, VEC);
+        if (int rc = check_grid(tl)) return rc;
+        tv_norm_strip_kernel<T, VEC, SCHEME, Z, TT, R><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.X, (T*)nullptr, (T*)nullptr, a.partial, a.P, tl);
+        count_launches(1);
+        PYTVB_CUDA(cudaGetLastError());
+        *a.nb = tl.nblocks;
+        return PYTVB_OK;
+    }
+};
+template <typename T>
+int run_tv_value(const pytvb_problem* pb, const void* x, double* d_tv, const void* lo, const void* hi, void* ws, cudaStream_t st) {
+    const Axes ax = axes_of(pb);
+    TvValArgs<T> a;
+    a.X = ImgView<T>{(const T*)x, (const T*)lo, (const T*)hi, 1};
+    a.partial = (double*)ws;
+    a.P = make_params<T>(pb);
+    a.st = st;
+    long long nb = 0;
+    a.nb = &nb;
+    const int vec = pick_vec<T>(pb, {x, lo, hi});
+    if (int rc = dispatch<LaunchTvVal, T>(vec, pb->scheme, ax.z_on, ax.t_on, a)) return rc;
+    return finalize_sum(a.partial, nb, d_tv, st);
+}
+}  // namespace
+
+extern "C" int pytvb_tv_value(const pytvb_problem* pb, const void* x, double* d_tv, const void* halo_lo, const void* halo_hi, void* ws, void* stream) {
+    if (int rc = check_problem(pb)) return rc;
+    PYTVB_REQUIRE(x && d_tv && ws, "x, d_tv and ws must not be NULL");
+    if (int rc = check_halos(pb, axes_of(pb).z_on, false, halo_lo, halo_hi)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    return pb->dtype == PYTVB_F32 ? run_tv_value<float>(pb, x, d_tv, halo_lo, halo_hi, ws, st) : run_tv_value<double>(pb, x, d_tv, halo_lo, halo_hi, ws, st);
+}
+
 extern "C" int pytvb_tv(const pytvb_problem* pb, const void* x, void* G, void* norms_or_null, double* d_tv, const void* halo_lo2,
                         const void* halo_hi2, void* ws_reduce, void* ws_tv, void* stream) {
     if (int rc = check_problem(pb)) return rc;

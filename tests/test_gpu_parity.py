@@ -508,6 +508,54 @@ def test_pipelined_host_streaming_equals_synchronous():
         assert torch.equal(outs_a[k], outs_b[k])
 
 
+def test_primal_dual_gap_and_stopping_rule():
+    """the gap P(x) - D(y) is non-negative, equals the oracle's value, shrinks, and stops `solve`."""
+    rs = np.random.RandomState(5)
+    x0 = cases.cp_volume() + 0.0
+    kw = dict(reg_z_over_reg=0.5, reg_time=0.25)
+    s = pytv.CPSolver(x0, lam=0.2, scheme="hybrid", variant="rof", **kw)
+    s.step(5)
+    p, d, g = s.gap()
+    x, y = s.x.cpu().numpy(), s.y.cpu().numpy()
+    p_o = 0.5 * np.sum((x - x0) ** 2) + 0.2 * orc.tv(x.copy(), "hybrid", **kw)[0]
+    d_o = 0.5 * np.sum(x0 ** 2) - 0.5 * np.sum((x0 - orc.D_T(y, "hybrid", **kw)) ** 2)
+    assert p == pytest.approx(p_o, rel=1e-12) and d == pytest.approx(d_o, rel=1e-12)
+    assert g >= 0
+    hist = []
+    info = s.solve(max_iter=3000, tol=1e-6, check_every=50, callback=lambda sol, it, P, D: hist.append(P - D))
+    assert info["converged"] and info["relative_gap"] <= 1e-6 and info["iterations"] < 3000
+    assert hist[-1] < hist[0]
+    # the solution is the TV prox of x0: TVProx with enough iterations lands on the same point
+    prox = pytv.TVProx(x0, lam=0.2, scheme="hybrid", n_iter=info["iterations"] + 55, **kw)
+    np.testing.assert_allclose(prox(x0).cpu().numpy(), s.x.cpu().numpy(), atol=1e-4)
+    # data-term hook: a new x0 with a warm dual start converges in fewer iterations than a cold start
+    x1 = x0 + 0.01 * rs.randn(*x0.shape)
+    warm = s.set_data(x1).solve(max_iter=3000, tol=1e-6, check_every=10)
+    cold = pytv.CPSolver(x1, lam=0.2, scheme="hybrid", variant="rof", **kw).solve(max_iter=3000, tol=1e-6, check_every=10)
+    assert warm["converged"] and cold["converged"] and warm["iterations"] <= cold["iterations"]
+
+
+def test_denoise_tv_chambolle_signature():
+    """README.md:260 TODO: a skimage-compatible entry point.  Checked against a long oracle run of the same ROF
+    problem (upwind = forward differences)."""
+    img = cases.synthetic_image(64)[0, 0] / 255.0
+    noisy = img + 0.1 * np.random.RandomState(1).randn(64, 64)
+    out = pytv.denoise_tv_chambolle(noisy, weight=0.1, eps=1e-7, max_num_iter=2000)
+    assert out.shape == noisy.shape and isinstance(out, np.ndarray)
+    x0 = noisy.reshape(1, 1, 64, 64)
+    x, xb, y = x0.copy(), x0.copy(), np.zeros((1, 2, 1, 64, 64))
+    for _ in range(3000):
+        x, xb, y, e = orc.cp_rof_step(x, xb, x0, y, "upwind", lam=0.1, sigma=0.5, tau=1.0 / 9.0)
+    np.testing.assert_allclose(out, x[0, 0], atol=2e-3)
+    assert np.mean((out - img) ** 2) < 0.5 * np.mean((noisy - img) ** 2)
+    rgb = np.stack([noisy, noisy[::-1], noisy.T], axis=-1).astype(np.float32)
+    out3 = pytv.denoise_tv_chambolle(rgb, weight=0.1, eps=0, max_num_iter=100, channel_axis=-1)
+    assert out3.shape == rgb.shape and out3.dtype == np.float32
+    np.testing.assert_allclose(out3[..., 0], pytv.denoise_tv_chambolle(rgb[..., 0], weight=0.1, eps=0, max_num_iter=100), atol=1e-5)
+    vol = np.random.RandomState(2).rand(8, 16, 16)
+    assert pytv.denoise_tv_chambolle(vol, weight=0.05, max_num_iter=20).shape == vol.shape
+
+
 # ------------------------------------------------------------------ slabs through the real kernels
 def _lib_call(fn, *a):
     _lib.check(fn(*a))
