@@ -55,11 +55,13 @@ def _worker(rank, world, port, scheme, variant, Nz, out_dir, overlap):
 
 @pytest.mark.parametrize("overlap", ["0", "1"], ids=["blocking", "overlap"])
 @pytest.mark.parametrize("variant", ["rof", "readme"])
-@pytest.mark.parametrize("scheme,world,Nz", [("hybrid", 2, 5), ("upwind", 2, 4), ("downwind", 2, 4), ("central", 2, 6), ("hybrid", 3, 7), ("hybrid", 3, 4), ("central", 3, 5)])
+@pytest.mark.parametrize("scheme,world,Nz", [("hybrid", 2, 5), ("upwind", 2, 4), ("downwind", 2, 4), ("central", 3, 5), ("hybrid", 3, 4)])
 def test_sharded_cp_equals_single_domain(tmp_path, scheme, world, Nz, variant, overlap):
     from oracle import tv_oracle as orc
-    if variant == "readme" and scheme != "hybrid":
+    if variant == "readme" and not (scheme == "hybrid" and world == 2):
         pytest.skip("README form is exercised with the hybrid scheme (its reference loop, README.md:145-157)")
+    if overlap == "1" and scheme in ("upwind", "downwind"):
+        pytest.skip("the overlapped schedule is exercised with the two-sided schemes")
     port = _free_port()
     mp.spawn(_worker, args=(world, port, scheme, variant, Nz, str(tmp_path), overlap), nprocs=world, join=True)
     x = np.concatenate([np.load(tmp_path / ("x_%d.npy" % r)) for r in range(world)], axis=0)

