@@ -110,6 +110,16 @@ int pytvb_cp_primal_readme(const pytvb_problem* pb, const void* y_tv, void* x, v
                            double sigma_A, double* d_fid_or_null, const void* halo_lo, const void* halo_hi, void* ws,
                            void* stream);
 
+/* Half-precision STORAGE of the dual field: float32 images and arithmetic, y kept as IEEE half in the
+ * same (Nz, Nd, M, Ni, Nj) layout, normalised to the unit ball (the array holds y / lam).  Halves the dominant
+ * traffic: 4(3Nd+5) -> 6Nd+20 bytes per voxel (68 instead of 116 for Nd = 8).  NOT within the 1e-5 parity
+ * tolerance (max error ~3e-4 on [0,1] images after 200 iterations): an opt-in mode.  ROF form only.  Field halo planes
+ * are half precision too. */
+int pytvb_cp_dual_f16y(const pytvb_problem* pb, const void* xbar, void* y_half, double lam, double sigma, double* d_l21_or_null,
+                       const void* halo_lo, const void* halo_hi, void* ws, void* stream);
+int pytvb_cp_primal_rof_f16y(const pytvb_problem* pb, const void* y_half, void* x, void* xbar, const void* x0, double lam, double tau,
+                             double theta, double* d_fid_or_null, const void* halo_lo_half, const void* halo_hi_half, void* ws, void* stream);
+
 /* Both passes of one iteration in ONE launch: pass-B tiles follow pass-A tiles a few z-planes behind (ordered by
  * tickets, synchronised by per-plane completion counters), so that pass B reads y from L2 instead of DRAM
  * (4(3Nd+5) -> 4(2Nd+5) bytes per voxel).  Same arithmetic and results as pytvb_cp_dual + pytvb_cp_primal_*.

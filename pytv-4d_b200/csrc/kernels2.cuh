@@ -34,13 +34,13 @@ inline Tiling make_strip_tiling(int Nj, int Ni, int M, int nz, int vec, int z_lo
     return t;
 }
 
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R>
-__global__ void __launch_bounds__(CTA_THREADS, PYTVB_DUAL_MINB) cp_dual_strip_kernel(ImgView<T> Xb, T* __restrict__ y, double* __restrict__ partial, Params<T> P, T sig,
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, typename YT = T>
+__global__ void __launch_bounds__(CTA_THREADS, PYTVB_DUAL_MINB) cp_dual_strip_kernel(ImgView<T> Xb, YT* __restrict__ y, double* __restrict__ partial, Params<T> P, T sig,
                                                                     T lam, Tiling tl) {
     const QuadIdx q = decode_quad(tl, (P.Ni + R - 1) / R, VEC);   // q.i = strip index
     T l21 = T(0);
     if (q.active) {
-        const DualPlane<T> pl = make_dual_plane<T, SCHEME>(Xb, y, P, q.z, q.t);
+        const DualPlane<T, YT> pl = make_dual_plane<T, SCHEME, YT>(Xb, y, P, q.z, q.t);
         const int i0 = q.i * R;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(CTA_THREADS, PYTVB_DUAL_MINB) cp_dual_strip_ke
                 const int o = i * P.Nj + q.j0;
                 const int o_up = i > 0 ? o - P.Nj : o;
                 const int o_dn = i < P.Ni - 1 ? o + P.Nj : o;
-                l21 += strip_quad_cp_dual<T, VEC, SCHEME, Z_ON, T_ON>(pl, P, i, q.j0, o, o_up, o_dn, sig, lam);
+                l21 += strip_quad_cp_dual<T, VEC, SCHEME, Z_ON, T_ON, YT>(pl, P, i, q.j0, o, o_up, o_dn, sig, lam);
             }
         }
     }
@@ -59,13 +59,13 @@ __global__ void __launch_bounds__(CTA_THREADS, PYTVB_DUAL_MINB) cp_dual_strip_ke
     }
 }
 
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int VARIANT, int R>
-__global__ void __launch_bounds__(CTA_THREADS, PYTVB_PRIMAL_MINB) cp_primal_strip_kernel(FieldView<T> Y, T* __restrict__ x, T* __restrict__ aux, const T* __restrict__ x0,
-                                                                      double* __restrict__ partial, Params<T> P, T tau, T c1, T c2, Tiling tl) {
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int VARIANT, int R, typename YT = T>
+__global__ void __launch_bounds__(CTA_THREADS, PYTVB_PRIMAL_MINB) cp_primal_strip_kernel(FieldView<YT> Y, T* __restrict__ x, T* __restrict__ aux, const T* __restrict__ x0,
+                                                                      double* __restrict__ partial, Params<T> P, T tau, T c1, T c2, Tiling tl, T tau_x0 = T(-1)) {
     const QuadIdx q = decode_quad(tl, (P.Ni + R - 1) / R, VEC);
     T fid = T(0);
     if (q.active) {
-        const PrimalPlane<T> pl = make_primal_plane<T, SCHEME, Z_ON, T_ON>(Y, P, q.z, q.t);
+        const PrimalPlane<T, YT> pl = make_primal_plane<T, SCHEME, Z_ON, T_ON, YT>(Y, P, q.z, q.t);
         const int i0 = q.i * R;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(CTA_THREADS, PYTVB_PRIMAL_MINB) cp_primal_stri
                 const int o = i * P.Nj + q.j0;
                 const int o_up = i > 0 ? o - P.Nj : o;
                 const int o_dn = i < P.Ni - 1 ? o + P.Nj : o;
-                fid += strip_quad_cp_primal<T, VEC, SCHEME, Z_ON, T_ON, VARIANT>(x, aux, x0, pl, P, i, q.j0, o, o_up, o_dn, tau, c1, c2);
+                fid += strip_quad_cp_primal<T, VEC, SCHEME, Z_ON, T_ON, VARIANT, false, YT>(x, aux, x0, pl, P, i, q.j0, o, o_up, o_dn, tau, c1, c2, tau_x0);
             }
         }
     }

@@ -14,6 +14,8 @@
 //   * the projection uses one rsqrt: scale = min(1, lam * rsqrt(|y|^2)); no division.
 // The functions are __host__ __device__ (plain loads only) so tests/emul runs them on the CPU too.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "tv_core.cuh"
 
 namespace pytvb {
@@ -37,19 +39,36 @@ PYTVB_HD float fast_sqrt(float a) {
 }
 PYTVB_HD double fast_sqrt(double a) { return sqrt(a); }
 
+// Loads / stores of the dual field y, which may be STORED in a narrower type than the arithmetic type T
+// (YT = __half: SURVEY 8f-4, halves the dominant Nd*V traffic; values are kept normalised to the unit ball so
+// that half precision's 11 significant bits cover them uniformly).
+template <typename T, typename YT, int VEC>
+PYTVB_HD void ld_y(T* dst, const YT* src) {
+    const Pack<YT, VEC> p = ld_pack<YT, VEC>(src);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) dst[e] = (T)p.v[e];
+}
+template <typename T, typename YT, int VEC>
+PYTVB_HD void st_y(YT* dst, const T* v) {
+    Pack<YT, VEC> p;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) p.v[e] = (YT)v[e];
+    st_pack<YT, VEC>(dst, p);
+}
+
 // Warp-uniform context of one (z, t) image plane for the dual pass.
-template <typename T>
+template <typename T, typename YT = T>
 struct DualPlane {
     const T* c;                       // plane (z, t) of xbar
     const T* zm; const T* zp;         // planes (z-1, t), (z+1, t): clamped to c at the volume boundary, halo planes at slab edges
     const T* tm; const T* tp;         // planes (z, t-1), (z, t+1), clamped
-    T* y;                             // component 0 of y at plane (z, t); component k at + k*sC
+    YT* y;                            // component 0 of y at plane (z, t); component k at + k*sC
     T fz, ft;                         // centred scheme only: 1 where the centred z / t difference exists, else 0
 };
 
-template <typename T, int SCHEME>
-PYTVB_HD DualPlane<T> make_dual_plane(const ImgView<T>& X, T* y, const Params<T>& P, int z, int t) {
-    DualPlane<T> d;
+template <typename T, int SCHEME, typename YT = T>
+PYTVB_HD DualPlane<T, YT> make_dual_plane(const ImgView<T>& X, YT* y, const Params<T>& P, int z, int t) {
+    DualPlane<T, YT> d;
     const long long zg = P.zg0 + z;
     const bool v_zm = zg > 0, v_zp = zg < P.NzG - 1, v_tm = t > 0, v_tp = t < P.M - 1;
     d.c = X.row(P, z, t, 0);
@@ -70,8 +89,8 @@ PYTVB_HD DualPlane<T> make_dual_plane(const ImgView<T>& X, T* y, const Params<T>
 
 // Raw differences of one quad: d[k][e] = weight * (x[k+1] - x[k]) etc. WITHOUT the scheme's global divisor.
 // o = i*Nj + j0; o_up / o_dn = offsets of rows i-1 / i+1 clamped to [0, Ni).
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON>
-PYTVB_HD void strip_raw_diffs(T (*d)[VEC], const DualPlane<T>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn) {
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, typename YT = T>
+PYTVB_HD void strip_raw_diffs(T (*d)[VEC], const DualPlane<T, YT>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn) {
     typedef Comp<SCHEME, Z_ON, T_ON> C;
     T c[VEC + 2], up[VEC], dn[VEC], zm[VEC], zp[VEC], tm[VEC], tp[VEC];
     ld_into<T, VEC>(c + 1, pl.c + o);
@@ -120,14 +139,14 @@ PYTVB_HD void strip_raw_diffs(T (*d)[VEC], const DualPlane<T>& pl, const Params<
 
 // One quad of the dual pass.  sig = sigma * inv_div (so that y + sigma*D = y + sig*raw_difference).
 // Returns sum_e sqrt(sum_k raw_k^2) (the caller multiplies the total by inv_div to get L21(D xbar)).
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON>
-PYTVB_HD T strip_quad_cp_dual(const DualPlane<T>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn, T sig, T lam) {
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, typename YT = T>
+PYTVB_HD T strip_quad_cp_dual(const DualPlane<T, YT>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn, T sig, T lam) {
     typedef Comp<SCHEME, Z_ON, T_ON> C;
     constexpr int ND = C::ND;
     T y[ND][VEC], d[ND][VEC];
 #pragma unroll
-    for (int k = 0; k < ND; ++k) ld_into<T, VEC>(y[k], pl.y + (long long)k * P.sC + o);
-    strip_raw_diffs<T, VEC, SCHEME, Z_ON, T_ON>(d, pl, P, i, j0, o, o_up, o_dn);
+    for (int k = 0; k < ND; ++k) ld_y<T, YT, VEC>(y[k], pl.y + (long long)k * P.sC + o);
+    strip_raw_diffs<T, VEC, SCHEME, Z_ON, T_ON, YT>(d, pl, P, i, j0, o, o_up, o_dn);
     T l21 = T(0);
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
@@ -146,12 +165,7 @@ PYTVB_HD T strip_quad_cp_dual(const DualPlane<T>& pl, const Params<T>& P, int i,
         for (int k = 0; k < ND; ++k) y[k][e] *= scale;
     }
 #pragma unroll
-    for (int k = 0; k < ND; ++k) {
-        Pack<T, VEC> pk;
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) pk.v[e] = y[k][e];
-        st_pack<T, VEC>(pl.y + (long long)k * P.sC + o, pk);
-    }
+    for (int k = 0; k < ND; ++k) st_y<T, YT, VEC>(pl.y + (long long)k * P.sC + o, y[k]);
     return l21;
 }
 
@@ -197,13 +211,13 @@ PYTVB_HD T strip_quad_tv_norm(T* w_plane, T* n_plane, const DualPlane<T>& pl, co
 
 // ------------------------------------------------------------------------------------------------
 // Warp-uniform context of one (z, t) plane for the primal pass.
-template <typename T>
+template <typename T, typename YT = T>
 struct PrimalPlane {
-    const T* y;        // component 0 of y at plane (z, t)
-    const T* zf_m;     // forward-type z component at plane z-1 (halo at a slab edge); any valid pointer when unused
-    const T* zb_p;     // backward-type z component at plane z+1
-    const T* tf_m;     // forward-type t component at plane t-1
-    const T* tb_p;     // backward-type t component at plane t+1
+    const YT* y;       // component 0 of y at plane (z, t)
+    const YT* zf_m;    // forward-type z component at plane z-1 (halo at a slab edge); any valid pointer when unused
+    const YT* zb_p;    // backward-type z component at plane z+1
+    const YT* tf_m;    // forward-type t component at plane t-1
+    const YT* tb_p;    // backward-type t component at plane t+1
     T az, bz, at, bt;  // weights * existence factors of the minus / plus z and t terms (see adjoint rule below)
     long long img;     // offset of image plane (z, t) in x / xbar / x0
 };
@@ -222,10 +236,10 @@ PYTVB_HD void adj_factors(T& a, T& b, long long k, long long L, bool fallback) {
     }
 }
 
-template <typename T, int SCHEME, bool Z_ON, bool T_ON>
-PYTVB_HD PrimalPlane<T> make_primal_plane(const FieldView<T>& Y, const Params<T>& P, int z, int t) {
+template <typename T, int SCHEME, bool Z_ON, bool T_ON, typename YT = T>
+PYTVB_HD PrimalPlane<T, YT> make_primal_plane(const FieldView<YT>& Y, const Params<T>& P, int z, int t) {
     typedef Comp<SCHEME, Z_ON, T_ON> C;
-    PrimalPlane<T> p;
+    PrimalPlane<T, YT> p;
     p.y = Y.row(P, z, 0, t, 0);
     p.img = (long long)z * P.sZ + (long long)t * P.sT;
     p.zf_m = p.zb_p = p.tf_m = p.tb_p = p.y;
@@ -269,32 +283,34 @@ template <> struct CgLoad<float, 1> { static __device__ __forceinline__ void ld(
 template <> struct CgLoad<double, 2> { static __device__ __forceinline__ void ld(double* d, const double* p) { const double2 v = __ldcg(reinterpret_cast<const double2*>(p)); d[0] = v.x; d[1] = v.y; } };
 template <> struct CgLoad<double, 1> { static __device__ __forceinline__ void ld(double* d, const double* p) { d[0] = __ldcg(p); } };
 #endif
-template <typename T, int VEC, bool CG>
-PYTVB_HD void ld_field(T* dst, const T* src) {
+template <typename T, int VEC, bool CG, typename YT>
+PYTVB_HD void ld_field(T* dst, const YT* src) {
 #if defined(__CUDA_ARCH__)
-    if constexpr (CG) { CgLoad<T, VEC>::ld(dst, src); return; }
+    if constexpr (CG) { CgLoad<T, VEC>::ld(dst, (const T*)src); return; }   // CG only with YT == T
 #endif
-    ld_into<T, VEC>(dst, src);
+    ld_y<T, YT, VEC>(dst, src);
 }
-template <typename T, bool CG>
-PYTVB_HD T ld_field1(const T* src) {
+template <typename T, bool CG, typename YT>
+PYTVB_HD T ld_field1(const YT* src) {
 #if defined(__CUDA_ARCH__)
-    if constexpr (CG) { T v; CgLoad<T, 1>::ld(&v, src); return v; }
+    if constexpr (CG) { T v; CgLoad<T, 1>::ld(&v, (const T*)src); return v; }
 #endif
-    return *src;
+    T v;
+    ld_y<T, YT, 1>(&v, src);
+    return v;
 }
 
 // D^T y at one quad (times inv_div), strip addressing.
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, bool CG = false>
-PYTVB_HD void strip_quad_DT(T* out, const PrimalPlane<T>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn) {
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, bool CG = false, typename YT = T>
+PYTVB_HD void strip_quad_DT(T* out, const PrimalPlane<T, YT>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn) {
     typedef Comp<SCHEME, Z_ON, T_ON> C;
     constexpr bool NF = (SCHEME != DOWNWIND);   // reads the forward-type slot at k-1 (centred: C[k-1])
     constexpr bool NB = (SCHEME != UPWIND);     // reads the backward-type slot at k+1 (centred: C[k+1])
     constexpr bool CTR = (SCHEME == CENTRAL);
-    const T* yI_F = pl.y + (long long)C::I_F * P.sC;
-    const T* yI_B = pl.y + (long long)C::I_B * P.sC;
-    const T* yJ_F = pl.y + (long long)C::J_F * P.sC;
-    const T* yJ_B = pl.y + (long long)C::J_B * P.sC;
+    const YT* yI_F = pl.y + (long long)C::I_F * P.sC;
+    const YT* yI_B = pl.y + (long long)C::I_B * P.sC;
+    const YT* yJ_F = pl.y + (long long)C::J_F * P.sC;
+    const YT* yJ_B = pl.y + (long long)C::J_B * P.sC;
     T acc[VEC];
     // ---- rows
     {
@@ -374,11 +390,13 @@ PYTVB_HD void strip_quad_DT(T* out, const PrimalPlane<T>& pl, const Params<T>& P
 
 // Primal update at one quad.  VARIANT 0: ROF prox + over-relaxation (aux = xbar); 1: README form (aux = y_f).
 // c1 = 1/(1+tau) (rof) or 1/(1+sigma_A) (readme); c2 = theta or sigma_A.  Returns sum (x_new - x0)^2.
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int VARIANT, bool CG = false>
-PYTVB_HD T strip_quad_cp_primal(T* x, T* aux, const T* x0, const PrimalPlane<T>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn,
-                                T tau, T c1, T c2) {
+// `tau` multiplies D^T y: for a normalised half-precision dual the caller passes tau * lam.
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int VARIANT, bool CG = false, typename YT = T>
+PYTVB_HD T strip_quad_cp_primal(T* x, T* aux, const T* x0, const PrimalPlane<T, YT>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn,
+                                T tau, T c1, T c2, T tau_x0 = T(-1)) {
     T dty[VEC];
-    strip_quad_DT<T, VEC, SCHEME, Z_ON, T_ON, CG>(dty, pl, P, i, j0, o, o_up, o_dn);
+    strip_quad_DT<T, VEC, SCHEME, Z_ON, T_ON, CG, YT>(dty, pl, P, i, j0, o, o_up, o_dn);
+    if (tau_x0 < T(0)) tau_x0 = tau;
     const long long off = pl.img + o;
     const Pack<T, VEC> xo = ld_pack<T, VEC>(x + off), x0q = ld_pack<T, VEC>(x0 + off);
     Pack<T, VEC> xn, ax;
@@ -386,7 +404,7 @@ PYTVB_HD T strip_quad_cp_primal(T* x, T* aux, const T* x0, const PrimalPlane<T>&
     if (VARIANT == 0) {
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
-            xn.v[e] = (xo.v[e] - tau * dty[e] + tau * x0q.v[e]) * c1;
+            xn.v[e] = (xo.v[e] - tau * dty[e] + tau_x0 * x0q.v[e]) * c1;
             ax.v[e] = xn.v[e] + c2 * (xn.v[e] - xo.v[e]);
             const T r = xn.v[e] - x0q.v[e];
             fid += r * r;

@@ -94,7 +94,8 @@ struct FieldView {
     const T* base;
     const T* lo;
     const T* hi;
-    PYTVB_HD const T* row(const Params<T>& P, int z, int comp, int t, int i) const {
+    template <typename PT>
+    PYTVB_HD const T* row(const PT& P, int z, int comp, int t, int i) const {
         const long long off = (long long)t * P.sT + (long long)i * P.Nj;
         if (z < 0) return lo + off;
         if (z >= P.Nz) return hi + off;

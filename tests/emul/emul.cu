@@ -314,6 +314,62 @@ extern "C" int pytvb_emulate(int op, const pytvb_problem* pb, const void* in, vo
     return pb->dtype == PYTVB_F32 ? run<float>(op, pb, in, out, out2, aux, x0, lo, hi, c0, c1, variant, force_scalar, sum)
                                   : run<double>(op, pb, in, out, out2, aux, x0, lo, hi, c0, c1, variant, force_scalar, sum);
 }
+// half-precision dual storage (float images), walked like the strip kernels
+template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct EDualH {
+    static int run(const EArgs<float>& a) {
+        double s = 0;
+        __half* y = (__half*)a.out;
+        for (int z = 0; z < a.P.Nz; ++z)
+            for (int t = 0; t < a.P.M; ++t) {
+                const DualPlane<float, __half> pl = make_dual_plane<float, SCHEME, __half>(a.X, y, a.P, z, t);
+                for (int i = 0; i < a.P.Ni; ++i)
+                    for (int j0 = 0; j0 < a.P.Nj; j0 += VEC) {
+                        const int o = i * a.P.Nj + j0, o_up = i > 0 ? o - a.P.Nj : o, o_dn = i < a.P.Ni - 1 ? o + a.P.Nj : o;
+                        // c0 = sigma, c1 = 1/lam
+                        s += (double)strip_quad_cp_dual<float, VEC, SCHEME, Z, TT, __half>(pl, a.P, i, j0, o, o_up, o_dn, a.c0 * a.c1 * a.P.inv_div, 1.0f);
+                    }
+            }
+        *a.sum = s * (double)a.P.inv_div;
+        return 0;
+    }
+};
+template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct EPrimalH {
+    static int run(const EArgs<float>& a) {
+        double s = 0;
+        // c0 = tau, c1 = theta, variant field carries nothing; lam is passed through a.z_lo as bits (see run_h)
+        const float lam = *(const float*)&a.z_lo;
+        const float c1 = 1.0f / (1.0f + a.c0);
+        FieldView<__half> Y{(const __half*)a.F.base, (const __half*)a.F.lo, (const __half*)a.F.hi};
+        for (int z = 0; z < a.P.Nz; ++z)
+            for (int t = 0; t < a.P.M; ++t) {
+                const PrimalPlane<float, __half> pl = make_primal_plane<float, SCHEME, Z, TT, __half>(Y, a.P, z, t);
+                for (int i = 0; i < a.P.Ni; ++i)
+                    for (int j0 = 0; j0 < a.P.Nj; j0 += VEC) {
+                        const int o = i * a.P.Nj + j0, o_up = i > 0 ? o - a.P.Nj : o, o_dn = i < a.P.Ni - 1 ? o + a.P.Nj : o;
+                        s += (double)strip_quad_cp_primal<float, VEC, SCHEME, Z, TT, 0, false, __half>(a.out, a.aux, a.x0, pl, a.P, i, j0, o, o_up, o_dn,
+                                                                                                        a.c0 * lam, c1, a.c1, a.c0);
+                    }
+            }
+        *a.sum = s;
+        return 0;
+    }
+};
+// op 0: dual (in = xbar, y_half in place, c0 = sigma, c1 = 1/lam);  op 1: primal (in = y_half, out = x, aux = xbar, x0, c0 = tau, c1 = theta, lam)
+extern "C" int pytvb_emulate_f16y(int op, const pytvb_problem* pb, const void* in, void* out, void* aux, const void* x0, double c0, double c1, double lam,
+                                  int force_scalar, double* sum) {
+    if (check_problem(pb) || pb->dtype != PYTVB_F32) return -1;
+    const Axes ax = axes_of(pb);
+    EArgs<float> a;
+    a.P = make_params<float>(pb);
+    a.out = (float*)out; a.aux = (float*)aux; a.x0 = (const float*)x0; a.c0 = (float)c0; a.c1 = (float)c1; a.sum = sum;
+    const float lamf = (float)lam;
+    a.z_lo = *(const int*)&lamf;
+    const int vec = vec_for<float>(pb, force_scalar);
+    if (op == 0) { a.X = ImgView<float>{(const float*)in, nullptr, nullptr, 1}; return dispatch<EDualH, float>(vec, pb->scheme, ax.z_on, ax.t_on, a); }
+    a.F = FieldView<float>{(const float*)in, nullptr, nullptr};
+    return dispatch<EPrimalH, float>(vec, pb->scheme, ax.z_on, ax.t_on, a);
+}
+
 template <typename T>
 int run_fused_emul(const pytvb_problem* pb, int variant, const void* u, void* y, void* x, void* aux, const void* x0, double lam, double sigma, double tau,
                    double c2, int lag, int force_scalar, const void* ilo, const void* ihi, const void* flo, const void* fhi, double* sums) {

@@ -127,6 +127,22 @@ def cp_fused(u, y, x, aux, x0, scheme, lam, sigma, tau, c2, variant, lag=3, scal
     return sums[0], sums[1]
 
 
+def cp_step_f16y(xbar, y_half, x, x0, scheme, lam, sigma, tau, theta, scalar=False, **w):
+    """One ROF iteration with the dual field stored as normalised half (numpy float16 array); returns (l21, fid)."""
+    pb, keep = _problem(scheme, x.dtype, x.shape, w.get("reg_z_over_reg", 1.0), w.get("reg_time", 0.0), w.get("mask_static", False),
+                        w.get("factor_reg_static", 0.0))
+    h = emul()
+    VP = ctypes.c_void_p
+    h.pytvb_emulate_f16y.restype = ctypes.c_int
+    h.pytvb_emulate_f16y.argtypes = [ctypes.c_int, ctypes.POINTER(_lib.Problem), VP, VP, VP, VP, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int,
+                                     ctypes.POINTER(ctypes.c_double)]
+    s = ctypes.c_double(0)
+    assert h.pytvb_emulate_f16y(0, ctypes.byref(pb), _ptr(xbar), _ptr(y_half), None, None, sigma, 1.0 / lam, lam, int(scalar), ctypes.byref(s)) == 0
+    l21 = s.value
+    assert h.pytvb_emulate_f16y(1, ctypes.byref(pb), _ptr(y_half), _ptr(x), _ptr(xbar), _ptr(x0), tau, theta, lam, int(scalar), ctypes.byref(s)) == 0
+    return l21, s.value
+
+
 class EmulOps:
     gen = 2
 

@@ -203,6 +203,32 @@ def test_fused_single_launch_schedule(scheme, shape, lag):
     assert 0.5 * fid + 0.1 * l21 == pytest.approx(e_ref, rel=1e-12)
 
 
+@pytest.mark.parametrize("scalar", [False, True], ids=["vec", "scalar"])
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_half_precision_dual_storage(scheme, scalar):
+    """y stored as y/lam in IEEE half: identical to the float32 oracle iteration with the normalised dual rounded to
+    half after every dual pass (storage is the only difference)."""
+    rs = np.random.RandomState(8)
+    shape = (3, 2, 6, 8)
+    x0 = rs.rand(*shape).astype(np.float32)
+    kw = dict(reg_z_over_reg=0.6, reg_time=0.4)
+    Nd = orc.num_components(scheme, 3, 2, 0.6, 0.4)
+    lam, sigma, tau, theta = 0.15, 0.5, 0.07, 1.0
+    x, xbar, yh = x0.copy(), x0.copy(), np.zeros((3, Nd, 2, 6, 8), np.float16)
+    xo, xbo, yo = x0.copy(), x0.copy(), np.zeros((3, Nd, 2, 6, 8), np.float32)
+    for _ in range(5):
+        l21, fid = em.cp_step_f16y(xbar, yh, x, x0, scheme, lam, sigma, tau, theta, scalar=scalar, **kw)
+        Dxb = orc.D(xbo, scheme, **kw)
+        yn = orc.project_l2_ball(yo + np.float32(sigma) * Dxb, lam)
+        yo = (yn / np.float32(lam)).astype(np.float16).astype(np.float32) * np.float32(lam)
+        xn = (xo - np.float32(tau) * orc.D_T(yo, scheme, **kw) + np.float32(tau) * x0) / np.float32(1 + tau)
+        xbo = xn + np.float32(theta) * (xn - xo)
+        xo = xn
+        assert l21 == pytest.approx(float(orc.l21(Dxb)), rel=1e-5)
+    np.testing.assert_allclose(x, xo, atol=3e-6)
+    np.testing.assert_allclose(yh.astype(np.float32) * lam, yo, atol=2e-4 * lam + 1e-7)
+
+
 @pytest.mark.parametrize("scheme", SCHEMES)
 def test_cp_slabs(scheme, gen):
     """One CP iteration computed slab by slab with halos equals the whole-volume iteration."""
