@@ -98,7 +98,7 @@ def _cpu_worker(args):
     return time.perf_counter() - t0, kind, e
 
 
-def cpu_baseline_single(sample_shape=(8, 4, 512, 512), steps=3, warmup=1):
+def cpu_baseline_single(sample_shape=(8, 4, 512, 512), steps=7, warmup=1):
     """Single-process run of the CPU implementation, as shipped (numpy element-wise kernels: one busy core)."""
     dt, kind, _ = _cpu_worker((1000, sample_shape, steps, warmup))
     vox = int(np.prod(sample_shape))
