@@ -262,6 +262,8 @@ def run_ours(args):
     for _ in range(W):
         solver.step()
         solver.energy()
+        if world > 1:
+            solver.energy_result(solver.energy_async())
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -287,8 +289,9 @@ def run_ours(args):
         ev[k][2].record()
         solver.iterations += 1
         if world > 1:
-            s = solver.scal.clone()
-            dist.all_reduce(s)          # scalar all-reduce for the energy, every iteration
+            pending_energy = solver.energy_async()     # scalar all-reduce for the energy, every iteration (own communicator)
+    if world > 1:
+        solver.energy_result(pending_energy)           # the last all-reduce lands inside the timed region
     end.record()
     barrier()
     launches = lib.pytvb_launch_count() - launches0

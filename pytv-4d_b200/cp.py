@@ -138,6 +138,14 @@ class HaloExchange:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         return t
 
+    def allreduce_sum_async(self, t):
+        """Scalar all-reduce on a communicator of its own, so that it never queues in front of the halo send/recv of
+        the next pass (one NCCL communicator executes its operations in order).  Returns the work handle."""
+        if getattr(self, "_reduce_group", None) is None:
+            ranks = list(range(self.dist.get_world_size())) if self.group is None else self.dist.get_process_group_ranks(self.group)
+            self._reduce_group = self.dist.new_group(ranks=ranks)      # collective: every rank of the solver gets here
+        return self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self._reduce_group, async_op=True)
+
 
 class CPSolver:
     """Device-resident Chambolle-Pock state for one volume, or for this rank's z-slab of a sharded volume.
@@ -461,6 +469,22 @@ class CPSolver:
         if self.halo is not None:
             s = s.to(self.x0.device)
             self.halo.allreduce_sum(s)
+        l21, fid = s.tolist()
+        return 0.5 * fid + self.lam * l21
+
+    def energy_async(self):
+        """Start the all-reduce of this iteration's energy terms without putting it on the critical path; returns a
+        handle for `energy_result`.  Single-GPU solvers just snapshot the scalars."""
+        if not self.track_energy:
+            raise RuntimeError("energy tracking was disabled")
+        s = torch.stack((self.scal[0:3].sum(), self.scal[3:6].sum()))
+        work = self.halo.allreduce_sum_async(s) if self.halo is not None else None
+        return (s, work)
+
+    def energy_result(self, handle):
+        s, work = handle
+        if work is not None:
+            work.wait()
         l21, fid = s.tolist()
         return 0.5 * fid + self.lam * l21
 

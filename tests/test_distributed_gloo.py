@@ -44,7 +44,9 @@ def _worker(rank, world, port, scheme, variant, Nz, out_dir, overlap):
         energies = []
         for _ in range(4):
             solver.step()
+            h = solver.energy_async()
             energies.append(solver.energy())
+            assert solver.energy_result(h) == energies[-1]
         np.save(os.path.join(out_dir, "x_%d.npy" % rank), solver.result())
         np.save(os.path.join(out_dir, "y_%d.npy" % rank), solver.y.numpy())
         if rank == 0:
