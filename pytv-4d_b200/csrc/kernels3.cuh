@@ -25,7 +25,7 @@
 // instead of 62.7 GB (pass B finds two thirds of y in L2) but runs at 5.2 TB/s instead of 6.5 TB/s, so an
 // iteration takes 9.69 ms against 9.60 ms for the two separate passes: a tie.  L = 1-2 wait too long for their
 // producers, L >= 4 loses the L2 hits; createpolicy evict_last / evict_first hints on y and finer tiles (R = 2)
-// did not help.  The kernel is therefore an option (PYTVB_FUSED=1 / CPSolver(fused=True)), not the default.
+// did not help, and prefetching pass B's x / x0 before its wait made it slower (10.1 ms).  The kernel is therefore an option (PYTVB_FUSED=1 / CPSolver(fused=True)), not the default.
 #pragma once
 #include "kernels2.cuh"
 
