@@ -14,4 +14,5 @@ from . import _lib            # noqa: F401  ctypes binding of libpytv_b200.so (l
 from . import tv_operators_GPU  # noqa: F401
 from . import tv_GPU          # noqa: F401
 from . import cp              # noqa: F401
+from . import sharded         # noqa: F401
 from .cp import CPSolver, TVProx, cp_denoise, denoise_tv_chambolle, partition_z  # noqa: F401

@@ -172,3 +172,46 @@ class EmulOps:
     def workspace(self, pb, device):
         import torch
         return torch.empty(1, dtype=torch.uint8)
+
+
+class EmulSlabOps:
+    """Executor for pytv_b200.sharded.ShardedTV on CPU tensors (host emulation of the strip kernels)."""
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+    def _run(self, op, pb, inp, out, out2=None, lo=None, hi=None):
+        s = ctypes.c_double(0.0)
+        rc = emul().pytvb_emulate(op, ctypes.byref(pb), self._p(inp), self._p(out), self._p(out2), None, None, self._p(lo), self._p(hi), 0.0, 0.0, 0, 0,
+                                  ctypes.byref(s))
+        assert rc == 0
+        return s.value
+
+    def D(self, pb, x, out, lo, hi):
+        self._run(7, pb, x, out, lo=lo, hi=hi)
+
+    def DT(self, pb, p, out, lo, hi):
+        self._run(8, pb, p, out, lo=lo, hi=hi)
+
+    def tv(self, pb, x, G, norms, d_tv, lo2, hi2):
+        d_tv[0] = self._run(9, pb, x, G, out2=norms, lo=lo2, hi=hi2)
+
+    def l21(self, pb, D, Nd, d_sum):
+        import torch
+        d_sum[0] = float(torch.sqrt((D.double() ** 2).sum(dim=1)).sum())
+
+    def apply_mask(self, pb, x, mask, is_plane):
+        import torch
+        m = mask.bool()
+        x[~(m.expand_as(x) if is_plane else m)] = 0
+
+    def to_device(self, arr):
+        import torch
+        t = arr if isinstance(arr, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(arr))
+        return t.contiguous()
+
+    def mask_static(self, ms, Ni, Nj):
+        import torch
+        m = ms if isinstance(ms, torch.Tensor) else torch.as_tensor(np.asarray(ms))
+        return (m.reshape(Ni, Nj) != 0).to(torch.uint8).contiguous()

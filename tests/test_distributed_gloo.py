@@ -91,3 +91,67 @@ def test_sharded_cp_equals_single_domain(tmp_path, scheme, world, Nz, variant, o
     np.testing.assert_allclose(x, xr, atol=1e-13)
     np.testing.assert_allclose(y, yr, atol=1e-13)
     np.testing.assert_allclose(energies, ref_e, rtol=1e-12)
+
+
+def _sharded_worker(rank, world, port, scheme, Nz, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import emul_helper as em
+    import pytv_b200
+    from pytv_b200.sharded import ShardedTV
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rs = np.random.RandomState(23)
+        M, N = 2, 8
+        x = rs.rand(Nz, M, N, N)
+        x[:, :, :2, :3] = 0.5
+        ms = rs.rand(1, 1, N, N) > 0.5
+        mask = rs.rand(N, N) > 0.2
+        off, cnt = pytv_b200.partition_z(Nz, world)[rank]
+        sh = ShardedTV(scheme, reg_z_over_reg=0.7, reg_time=0.3, mask_static=ms, factor_reg_static=2.0, ops=em.EmulSlabOps())
+        xs = torch.as_tensor(x[off:off + cnt].copy())
+        Ds = sh.D(xs)
+        p = rs.randn(Nz, Ds.shape[1], M, N, N)
+        DTs = sh.D_T(torch.as_tensor(p[off:off + cnt].copy()))
+        l21 = sh.l21(Ds)
+        tv, G, norms = sh.tv(xs.clone(), return_grad_norms=True)
+        tvm, Gm = sh.tv(xs, mask=torch.as_tensor(mask))
+        np.savez(os.path.join(out_dir, "r%d.npz" % rank), D=Ds.numpy(), DT=DTs.numpy(), G=G.numpy(), norms=norms.numpy(), Gm=Gm.numpy(), xm=xs.numpy(),
+                 scal=np.array([l21, tv, tvm]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("scheme,world,Nz", [("hybrid", 2, 5), ("central", 3, 7), ("upwind", 2, 4), ("downwind", 2, 4)])
+def test_sharded_operators_and_tv_equal_whole_volume(tmp_path, scheme, world, Nz):
+    """pytv_b200.sharded.ShardedTV over gloo: D, D_T, L21 and tv (value, sub-gradient, norms, in-place mask) of the slabs
+    equal the whole-volume oracle."""
+    from oracle import tv_oracle as orc
+    mp.spawn(_sharded_worker, args=(world, _free_port(), scheme, Nz, str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(tmp_path / ("r%d.npz" % r)) for r in range(world)]
+    cat = lambda k: np.concatenate([p[k] for p in parts], axis=0)
+    rs = np.random.RandomState(23)
+    M, N = 2, 8
+    x = rs.rand(Nz, M, N, N)
+    x[:, :, :2, :3] = 0.5
+    ms = rs.rand(1, 1, N, N) > 0.5
+    mask = rs.rand(N, N) > 0.2
+    kw = dict(reg_z_over_reg=0.7, reg_time=0.3, mask_static=ms, factor_reg_static=2.0)
+    D_o = orc.D(x, scheme, **kw)
+    p = rs.randn(*D_o.shape)
+    np.testing.assert_allclose(cat("D"), D_o, atol=1e-14)
+    np.testing.assert_allclose(cat("DT"), orc.D_T(p, scheme, **kw), atol=1e-13)
+    tv_o, G_o, n_o = orc.tv(x.copy(), scheme, return_grad_norms=True, **kw)
+    for part in parts:
+        assert part["scal"][0] == pytest.approx(float(orc.l21(D_o)), rel=1e-13)
+        assert part["scal"][1] == pytest.approx(tv_o, rel=1e-13)
+    np.testing.assert_allclose(cat("G"), G_o, atol=1e-12)
+    np.testing.assert_allclose(cat("norms"), n_o, atol=1e-13)
+    xm = x.copy()
+    tvm_o, Gm_o = orc.tv(xm, scheme, mask=np.broadcast_to(mask, x.shape), **kw)
+    np.testing.assert_array_equal(cat("xm"), xm)
+    np.testing.assert_allclose(cat("Gm"), Gm_o, atol=1e-12)
+    assert parts[0]["scal"][2] == pytest.approx(tvm_o, rel=1e-13)

@@ -63,3 +63,55 @@ def test_two_gpu_sharded_cp_equals_single_gpu(tmp_path, scheme, overlap):
         energies.append(s.energy())
     np.testing.assert_array_equal(x, s.result())
     np.testing.assert_allclose(np.load(tmp_path / "e.npy"), energies, rtol=1e-12)
+
+
+def _sharded_worker(rank, world, port, scheme, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import pytv_b200
+    from pytv_b200.sharded import ShardedTV
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        g = torch.Generator().manual_seed(5)
+        x = torch.rand(10, 3, 64, 64, generator=g)
+        ms = torch.rand(1, 1, 64, 64, generator=g) > 0.5
+        off, cnt = pytv_b200.partition_z(10, world)[rank]
+        sh = ShardedTV(scheme, reg_z_over_reg=0.7, reg_time=0.3, mask_static=ms, factor_reg_static=2.0)
+        xs = x[off:off + cnt].cuda()
+        Ds = sh.D(xs)
+        p = torch.randn(10, Ds.shape[1], 3, 64, 64, generator=g)
+        DTs = sh.D_T(p[off:off + cnt].cuda())
+        l21 = sh.l21(Ds)
+        tv, G, norms = sh.tv(xs, return_grad_norms=True)
+        np.savez(os.path.join(out_dir, "s%d.npz" % rank), D=Ds.cpu().numpy(), DT=DTs.cpu().numpy(), G=G.cpu().numpy(), norms=norms.cpu().numpy(),
+                 scal=np.array([l21, tv]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("scheme", ["hybrid", "central", "downwind"])
+def test_two_gpu_sharded_operators_equal_single_gpu(tmp_path, scheme):
+    """ShardedTV over NCCL on two GPUs: bitwise the single-GPU drop-in results on the whole volume."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import pytv_b200 as pytv
+    mp.spawn(_sharded_worker, args=(2, _free_port(), scheme, str(tmp_path)), nprocs=2, join=True)
+    parts = [np.load(tmp_path / ("s%d.npz" % r)) for r in range(2)]
+    cat = lambda k: np.concatenate([q[k] for q in parts], axis=0)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(10, 3, 64, 64, generator=g)
+    ms = torch.rand(1, 1, 64, 64, generator=g) > 0.5
+    kw = dict(reg_z_over_reg=0.7, reg_time=0.3, mask_static=ms, factor_reg_static=2.0)
+    D1 = getattr(pytv.tv_operators_GPU, "D_" + scheme)(x.cuda(), **kw)
+    p = torch.randn(10, D1.shape[1], 3, 64, 64, generator=g)
+    DT1 = getattr(pytv.tv_operators_GPU, "D_T_" + scheme)(p.cuda(), **kw)
+    tv1, G1, n1 = getattr(pytv.tv_GPU, "tv_" + scheme)(x.cuda(), return_pytorch_tensor=True, return_grad_norms=True, **kw)
+    np.testing.assert_array_equal(cat("D"), D1.cpu().numpy())
+    np.testing.assert_array_equal(cat("DT"), DT1.cpu().numpy())
+    np.testing.assert_array_equal(cat("G"), G1.cpu().numpy())
+    np.testing.assert_array_equal(cat("norms"), n1.cpu().numpy())
+    assert parts[0]["scal"][1] == pytest.approx(float(tv1), rel=1e-6)
+    assert parts[0]["scal"][0] == pytest.approx(float(pytv.tv_operators_GPU.compute_L21_norm(D1)), rel=1e-6)
