@@ -114,8 +114,11 @@ static __global__ void fused_check_kernel(const unsigned* error, double* d_l21, 
     }
 }
 
+#ifndef PYTVB_FUSED_MINB
+#define PYTVB_FUSED_MINB PYTVB_DUAL_MINB
+#endif
 template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int VARIANT, int R>
-__global__ void __launch_bounds__(CTA_THREADS, PYTVB_DUAL_MINB)
+__global__ void __launch_bounds__(CTA_THREADS, PYTVB_FUSED_MINB)
 cp_fused_kernel(ImgView<T> Xin, FieldView<T> Y, T* __restrict__ y, T* __restrict__ x, T* __restrict__ aux, const T* __restrict__ x0,
                 double* __restrict__ partialA, double* __restrict__ partialB, Params<T> P, T sig, T lam, T tau, T c1, T c2, FusedSched s, FusedCtl ctl) {
     __shared__ unsigned s_ticket;
