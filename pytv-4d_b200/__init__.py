@@ -15,4 +15,4 @@ from . import tv_operators_GPU  # noqa: F401
 from . import tv_GPU          # noqa: F401
 from . import cp              # noqa: F401
 from . import sharded         # noqa: F401
-from .cp import CPSolver, TVProx, cp_denoise, denoise_tv_chambolle, partition_z  # noqa: F401
+from .cp import CPSolver, TVProx, cp_denoise, denoise_tv_chambolle, gd_denoise, partition_z  # noqa: F401

@@ -643,6 +643,37 @@ def denoise_tv_chambolle(image, weight=0.1, eps=2e-4, max_num_iter=200, channel_
     return out if was_tensor else out.cpu().numpy()
 
 
+def gd_denoise(x0, lam, n_iter, step, scheme="hybrid", return_pytorch_tensor=False, return_losses=False, **weights):
+    """The README's sub-gradient descent loop (README.md:107-124) with the state resident on the device:
+        tv, G = tv_<scheme>(x);  x <- x - step ((x - x0) + lam G);  loss = 0.5 |x - x0|^2 + lam tv
+    `weights`: reg_z_over_reg, reg_time, mask_static, factor_reg_static.  Returns x (and the loss history, one entry per
+    iteration, read back once at the end)."""
+    from . import tv_GPU   # noqa: F401  (same kernels as the drop-in call)
+    x0d, was_tensor = _dev.to_device(x0)
+    shape = _dev.image_shape(x0d)
+    lib = _lib.lib()
+    ms = _dev.mask_static_to_device(weights.get("mask_static", False), shape[2], shape[3])
+    pb = _dev.problem(scheme, x0d, shape, weights.get("reg_z_over_reg", 1.0), weights.get("reg_time", 0.0), weights.get("factor_reg_static", 0), ms)
+    x = x0d.clone()
+    G = torch.empty_like(x)
+    ws_r = _dev.reduce_workspace(pb, x.device)
+    ws_t = torch.empty(lib.pytvb_tv_workspace_bytes(ctypes.byref(pb)), dtype=torch.uint8, device=x.device)
+    tvs = torch.zeros(int(n_iter), dtype=torch.float64, device=x.device)
+    fids = torch.zeros(int(n_iter), dtype=torch.float64, device=x.device)
+    st = _dev.stream_ptr()
+    for it in range(int(n_iter)):
+        _lib.check(lib.pytvb_tv(ctypes.byref(pb), _dev.ptr(x), _dev.ptr(G), None, _dev.ptr(tvs[it:it + 1]), None, None, _dev.ptr(ws_r), _dev.ptr(ws_t), st))
+        # x += -step * ((x - x0) + lam * G)
+        G.mul_(lam).add_(x).sub_(x0d)
+        x.add_(G, alpha=-float(step))
+        if return_losses:
+            fids[it] = torch.sum((x - x0d).double() ** 2)
+    out = x if (return_pytorch_tensor or was_tensor) else x.cpu().numpy()
+    if return_losses:
+        return out, (0.5 * fids + float(lam) * tvs).cpu().numpy()
+    return out
+
+
 def cp_denoise(x0, lam, n_iter, scheme="hybrid", variant="rof", return_pytorch_tensor=False, return_energy=False, **kw):
     """Denoise `x0` with n_iter fused Chambolle-Pock iterations; see CPSolver for the keyword arguments."""
     solver = CPSolver(x0, lam, scheme=scheme, variant=variant, track_energy=return_energy, **kw)

@@ -505,6 +505,16 @@ def test_cp_and_gd_loops_synthetic(golden_kat):
         assert float(loss) == pytest.approx(g["losses"][it], rel=1e-11)
 
 
+def test_gd_denoise_matches_readme_loop(golden_kat):
+    """README.md:107-124 as a device-resident call: the first 50 losses of the reference loop (float64)."""
+    x_true = cases.synthetic_image(64)
+    noisy = x_true + 100 * np.random.RandomState(0).rand(*x_true.shape)
+    g = golden_kat["gd_synthetic64"]
+    x, losses = pytv.gd_denoise(noisy, 25.0, 50, 5e-3, scheme="hybrid", return_losses=True)
+    np.testing.assert_allclose(losses, g["losses"], rtol=1e-10)
+    assert x.sum() == pytest.approx(g["sum_x"], rel=1e-11)
+
+
 def test_cp_denoise_converges_and_reduces_energy():
     """BASELINE config 3 in miniature: piecewise-constant 3-D phantom + noise, hybrid, float32."""
     torch.manual_seed(0)
