@@ -52,6 +52,9 @@ typedef struct pytvb_problem {
     double reg_time;            /* weight of the time differences; <= 0: time axis off */
     double factor_reg_static;   /* time weight multiplier where mask_static is set */
     const uint8_t* mask_static; /* device (Ni, Nj) bytes, nonzero = static pixel; NULL = none */
+    const void* time_scale;     /* EXTENSION (reference TODO, README.md:258): device (Nz, M, Ni, Nj) array of `dtype`, the per-voxel factor
+                                 * of the time component(s) = sqrt of a weight map; multiplies on top of mask_static; NULL = none.
+                                 * Not available for slabs with z halos in pytvb_tv, nor with PYTVB_GEN=1. */
 } pytvb_problem;
 
 int pytvb_version(void);

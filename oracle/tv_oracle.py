@@ -138,7 +138,18 @@ def _mask_plane(mask_static, N_i, N_j):
 
 
 # ----------------------------------------------------------------------------- operators
-def D(img, scheme, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_reg_static=0.0):
+def _time_scale(time_weight, shape, dt):
+    """EXTENSION (the reference's TODO, README.md:258: "replace mask_static, factor_reg_static with a weight matrix of
+    size Nz x M x N x N"): per-voxel weight of the time regularisation; like reg_time it enters as its square root,
+    applied to the time component(s) at the voxel where the component lives.  No reference implementation exists:
+    pinned only by adjointness and by its reduction to mask_static for weights in {1, factor} (tests)."""
+    if time_weight is None:
+        return None
+    w = np.asarray(time_weight, dtype=np.float64)
+    return np.sqrt(np.broadcast_to(w, shape)).astype(dt)
+
+
+def D(img, scheme, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_reg_static=0.0, time_weight=None):
     """Forward operator of `scheme`: (Nz,M,N,N) -> (Nz,Nd,M,N,N).
     Restates D_upwind / D_downwind / D_central / D_hybrid (tv_operators_CPU.py:222, :156, :288, :76)."""
     img = np.asarray(img)
@@ -150,6 +161,7 @@ def D(img, scheme, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_r
     s_t = dt.type(np.sqrt(reg_time)) if reg_time > 0 else dt.type(0)
     s_f = dt.type(np.sqrt(factor_reg_static))
     mplane = _mask_plane(mask_static, Ni, Nj)
+    tsc = _time_scale(time_weight, img.shape, dt)
     for d, (axis, kind) in enumerate(comps):
         c = _difference(img, axis, kind)
         if axis == _AX_Z:
@@ -158,6 +170,8 @@ def D(img, scheme, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_r
             c = s_t * c                                    # :278
             if mplane is not None:                         # :280-282
                 c = np.where(mplane[None, None], c * s_f, c)
+            if tsc is not None:
+                c = c * tsc
         out[:, d] = c
     div = _global_divisor(scheme, dt)
     if div is not None:
@@ -165,7 +179,7 @@ def D(img, scheme, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_r
     return out
 
 
-def D_T(p, scheme, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_reg_static=0.0):
+def D_T(p, scheme, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_reg_static=0.0, time_weight=None):
     """Adjoint operator: (Nz,Nd,M,N,N) -> (Nz,M,N,N).
     Restates D_T_upwind / D_T_downwind / D_T_central / D_T_hybrid (tv_operators_CPU.py:518, :450, :585, :360)."""
     p = np.asarray(p)
@@ -179,13 +193,15 @@ def D_T(p, scheme, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_r
     s_f = dt.type(np.sqrt(factor_reg_static))
     out = np.zeros((Nz, M, Ni, Nj), dtype=dt)
     time_part = None
+    tsc = _time_scale(time_weight, out.shape, dt)
     for d, (axis, kind) in enumerate(comps):
         if axis == _AX_Z:
             _adjoint_accumulate(out, p[:, d], axis, kind, s_z)          # :565-566
         elif axis == _AX_T:
             if time_part is None:
                 time_part = np.zeros_like(out)                          # :571
-            _adjoint_accumulate(time_part, p[:, d], axis, kind, s_t)    # :573-574
+            pd = p[:, d] if tsc is None else p[:, d] * tsc              # exact adjoint: the scale sits where the component lives
+            _adjoint_accumulate(time_part, pd, axis, kind, s_t)         # :573-574
         else:
             _adjoint_accumulate(out, p[:, d], axis, kind)
     if time_part is not None:
@@ -209,7 +225,7 @@ def l21(D_img, return_array=False):
 
 # ----------------------------------------------------------------------------- direct API
 def tv(img, scheme, mask=None, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False,
-       factor_reg_static=0.0, return_grad_norms=False):
+       factor_reg_static=0.0, return_grad_norms=False, time_weight=None):
     """TV value and the reference's subgradient (tv_hybrid/tv_downwind/tv_upwind/tv_central,
     tv_CPU.py:47, :131, :195, :258).
 
@@ -222,7 +238,7 @@ def tv(img, scheme, mask=None, reg_z_over_reg=1.0, reg_time=0.0, mask_static=Fal
         m = np.broadcast_to(np.asarray(mask).astype(bool), img.shape)
         img[~m] = 0
     Nz, M, Ni, Nj = img.shape
-    field = D(img, scheme, reg_z_over_reg, reg_time, mask_static, factor_reg_static)
+    field = D(img, scheme, reg_z_over_reg, reg_time, mask_static, factor_reg_static, time_weight)
     value, norms = l21(field, return_array=True)
     norms[norms == 0] = np.inf
     comps = components(scheme, Nz, M, reg_z_over_reg, reg_time)

@@ -49,10 +49,22 @@ def image_shape(img):
     return tuple(int(s) for s in img.shape)
 
 
-def problem(scheme, t, shape, reg_z_over_reg, reg_time, factor_reg_static, ms, z_offset=0, Nz_global=None):
+def time_scale_to_device(time_weight, shape, like):
+    """EXTENSION (reference TODO, README.md:258): a (Nz, M, N, N) weight map of the time regularisation -> its square
+    root as a contiguous device array of the compute dtype (what the C ABI takes as `time_scale`), or None."""
+    if time_weight is None:
+        return None
+    w = time_weight if isinstance(time_weight, torch.Tensor) else torch.as_tensor(np.asarray(time_weight))
+    w = torch.broadcast_to(w.to(like.device).to(torch.float64), tuple(shape))
+    if bool((w < 0).any()):
+        raise ValueError("time_weight must be >= 0")
+    return torch.sqrt(w).to(like.dtype).contiguous()
+
+
+def problem(scheme, t, shape, reg_z_over_reg, reg_time, factor_reg_static, ms, z_offset=0, Nz_global=None, ts=None):
     rz = float(reg_z_over_reg)
     return _lib.make_problem(scheme, dtype_id(t), shape, rz, float(reg_time), float(factor_reg_static),
-                             ms.data_ptr() if ms is not None else None, z_offset, Nz_global)
+                             ms.data_ptr() if ms is not None else None, z_offset, Nz_global, ts.data_ptr() if ts is not None else None)
 
 
 def ptr(t):

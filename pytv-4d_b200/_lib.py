@@ -29,16 +29,18 @@ class Problem(ctypes.Structure):
         ("reg_time", ctypes.c_double),
         ("factor_reg_static", ctypes.c_double),
         ("mask_static", ctypes.c_void_p),
+        ("time_scale", ctypes.c_void_p),
     ]
 
 
 def make_problem(scheme, dtype_id, shape, reg_z_over_reg=1.0, reg_time=0.0, factor_reg_static=0.0, mask_static_ptr=None,
-                 z_offset=0, Nz_global=None):
+                 z_offset=0, Nz_global=None, time_scale_ptr=None):
     Nz, M, Ni, Nj = (int(s) for s in shape)
     rz = float(reg_z_over_reg)
     return Problem(SCHEME_ID[scheme] if isinstance(scheme, str) else int(scheme), int(dtype_id), Nz, M, Ni, Nj, int(z_offset),
                    int(Nz if Nz_global is None else Nz_global), rz, float(reg_time), float(factor_reg_static),
-                   ctypes.c_void_p(mask_static_ptr) if mask_static_ptr else None)
+                   ctypes.c_void_p(mask_static_ptr) if mask_static_ptr else None,
+                   ctypes.c_void_p(time_scale_ptr) if time_scale_ptr else None)
 
 
 _VP = ctypes.c_void_p

@@ -157,7 +157,7 @@ class CPSolver:
 
     def __init__(self, x0, lam, scheme="hybrid", variant="rof", sigma=0.5, tau=None, theta=1.0, sigma_A=1.0, reg_z_over_reg=1.0,
                  reg_time=0.0, mask_static=False, factor_reg_static=0, distributed=False, group=None, z_offset=None, Nz_global=None,
-                 ops=None, track_energy=True, fused=None, dual_dtype=None):
+                 ops=None, track_energy=True, fused=None, dual_dtype=None, time_weight=None):
         if scheme not in _dev.SCHEMES:
             raise ValueError("unknown scheme %r" % (scheme,))
         if variant not in ("rof", "readme"):
@@ -194,9 +194,14 @@ class CPSolver:
             else:
                 m = mask_static if isinstance(mask_static, torch.Tensor) else torch.as_tensor(np.asarray(mask_static))
                 self._ms = (m.reshape(shape[2], shape[3]) != 0).to(torch.uint8).contiguous()
+        # extension (reference TODO, README.md:258): per-voxel weight map of the time regularisation for this slab
+        self._ts = None
+        if time_weight is not None:
+            w = time_weight if isinstance(time_weight, torch.Tensor) else torch.as_tensor(np.asarray(time_weight))
+            self._ts = torch.sqrt(torch.broadcast_to(w.to(dev).to(torch.float64), shape)).to(dt).contiguous()
         self.pb = _lib.make_problem(scheme, _lib.F32 if dt == torch.float32 else _lib.F64, shape, float(reg_z_over_reg), float(reg_time),
                                     float(factor_reg_static), self._ms.data_ptr() if self._ms is not None else None, self.z_offset,
-                                    self.Nz_global)
+                                    self.Nz_global, self._ts.data_ptr() if self._ts is not None else None)
         self.z_on = self.Nz_global > 1 and float(reg_z_over_reg) > 0
         self.t_on = shape[1] > 1 and float(reg_time) > 0
         self.Nd = (4 + 2 * self.z_on + 2 * self.t_on) if scheme == "hybrid" else (2 + self.z_on + self.t_on)
@@ -277,6 +282,8 @@ class CPSolver:
             pb = _lib.Problem.from_buffer_copy(self.pb)
             pb.Nz = b - a
             pb.z_offset = self.z_offset + a
+            if self._ts is not None:
+                pb.time_scale = self._ts[a].data_ptr()
             self._pb_cache[key] = pb
         return pb
 

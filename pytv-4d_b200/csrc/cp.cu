@@ -189,6 +189,7 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchPrimalH
 // vector width: 4 floats / 4 halves per quad need 16-byte images and 8-byte field pointers
 inline int pick_vec_h(const pytvb_problem* pb, std::initializer_list<const void*> f32, std::initializer_list<const void*> f16) {
     if (pb->Nj % 4 != 0) return 1;
+    if (pb->time_scale && (reinterpret_cast<uintptr_t>(pb->time_scale) % 16) != 0) return 1;
     for (const void* p : f32) if (p && (reinterpret_cast<uintptr_t>(p) % 16) != 0) return 1;
     for (const void* p : f16) if (p && (reinterpret_cast<uintptr_t>(p) % 8) != 0) return 1;
     return 4;

@@ -46,6 +46,7 @@ int pytvb_tv_host(const pytvb_problem* pb, const void* x_host, void* G_host, voi
     if (int rc = check_problem(pb)) return rc;
     PYTVB_REQUIRE(x_host && G_host && tv_out, "x_host, G_host and tv_out must not be NULL");
     PYTVB_REQUIRE(pb->z_offset == 0 && pb->Nz_global == pb->Nz, "pytvb_tv_host works on whole volumes");
+    PYTVB_REQUIRE(!pb->time_scale, "time_scale is not supported by the host-buffer entry points");
     cudaStream_t st = nullptr;
     const size_t nb = voxels(pb) * elem_size(pb);
     DeviceBuf mask, x, G, norms, wsr, wst, dtv;
@@ -70,6 +71,7 @@ int pytvb_cp_create(const pytvb_problem* pb, double lam, double sigma, double ta
     if (int rc = check_problem(pb)) return rc;
     PYTVB_REQUIRE(out, "out must not be NULL");
     PYTVB_REQUIRE(pb->z_offset == 0 && pb->Nz_global == pb->Nz, "the host-buffer solver works on whole volumes");
+    PYTVB_REQUIRE(!pb->time_scale, "time_scale is not supported by the host-buffer entry points");
     PYTVB_REQUIRE(lam >= 0 && sigma > 0 && tau > 0, "lam >= 0, sigma > 0, tau > 0 required");
     pytvb_cp_solver* s = new (std::nothrow) pytvb_cp_solver();
     PYTVB_REQUIRE(s, "out of host memory");

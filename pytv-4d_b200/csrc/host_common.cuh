@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/pytv_b200.h"
@@ -58,6 +59,10 @@ inline int check_problem(const pytvb_problem* pb) {
     PYTVB_REQUIRE(pb->z_offset >= 0 && pb->z_offset + pb->Nz <= pb->Nz_global, "slab [%lld, %lld) outside 0..%lld",
                   (long long)pb->z_offset, (long long)(pb->z_offset + pb->Nz), (long long)pb->Nz_global);
     PYTVB_REQUIRE(!(pb->factor_reg_static < 0), "factor_reg_static must be >= 0");
+    {
+        const char* g = getenv("PYTVB_GEN");
+        PYTVB_REQUIRE(!(pb->time_scale && g && atoi(g) < 2), "time_scale is implemented by the generation-2 kernels only (unset PYTVB_GEN)");
+    }
     return PYTVB_OK;
 }
 
@@ -75,6 +80,7 @@ inline Params<T> make_params(const pytvb_problem* pb) {
     P.div = pb->scheme == PYTVB_HYBRID ? (T)sqrt(2.0) : (pb->scheme == PYTVB_CENTRAL ? T(2) : T(1));
     P.inv_div = T(1) / P.div;
     P.mask_static = a.t_on ? pb->mask_static : nullptr;
+    P.tscale = a.t_on ? (const T*)pb->time_scale : nullptr;
     P.sT = (long long)pb->Ni * pb->Nj;
     P.sZ = P.sT * pb->M;
     P.sC = P.sZ;
@@ -87,6 +93,7 @@ template <typename T>
 inline int pick_vec(const pytvb_problem* pb, std::initializer_list<const void*> ptrs) {
     constexpr int VM = VecOf<T>::value;
     if (pb->Nj % VM != 0) return 1;
+    if (pb->time_scale && (reinterpret_cast<uintptr_t>(pb->time_scale) % (VM * sizeof(T))) != 0) return 1;
     for (const void* p : ptrs)
         if (p && (reinterpret_cast<uintptr_t>(p) % (VM * sizeof(T))) != 0) return 1;
     return VM;

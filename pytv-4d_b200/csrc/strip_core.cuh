@@ -75,6 +75,7 @@ struct DualPlane {
     const T* tm; const T* tp;         // planes (z, t-1), (z, t+1), clamped
     YT* y;                            // component 0 of y at plane (z, t); component k at + k*sC
     T fz, ft;                         // centred scheme only: 1 where the centred z / t difference exists, else 0
+    const T* ts;                      // plane (z, t) of the per-voxel time scale, or null
 };
 
 template <typename T, int SCHEME, typename YT = T>
@@ -89,6 +90,7 @@ PYTVB_HD DualPlane<T, YT> make_dual_plane(const ImgView<T>& X, YT* y, const Para
     d.tp = v_tp ? X.row(P, z, t + 1, 0) : d.c;
     d.y = y + (long long)z * P.sZf + (long long)t * P.sT;
     d.fz = d.ft = T(1);
+    d.ts = (P.tscale && z >= 0 && z < P.Nz) ? P.tscale + (long long)z * P.sZ + (long long)t * P.sT : nullptr;
     if (SCHEME == CENTRAL) {
         // centred difference exists iff both neighbours do; on a length-2 axis it degrades to the forward
         // difference (minus pointer := centre, the clamped plus pointer already gives 0 on the last plane)
@@ -96,6 +98,26 @@ PYTVB_HD DualPlane<T, YT> make_dual_plane(const ImgView<T>& X, YT* y, const Para
         if (P.t_fwd_fallback) d.tm = d.c; else d.ft = (v_tm && v_tp) ? T(1) : T(0);
     }
     return d;
+}
+
+// Factor of the time component(s) at a quad: sqrt(factor_reg_static) on static pixels (tv_operators_CPU.py:148-150)
+// times the per-voxel time scale, if any (extension: the reference's TODO README.md:258).
+template <typename T, int VEC>
+PYTVB_HD void time_factor(T* f, const Params<T>& P, const T* ts_plane, int i, int j0, int o) {
+    static_factor<T, VEC>(f, P, i, j0);
+    if (ts_plane) {
+        const Pack<T, VEC> sc = ld_pack<T, VEC>(ts_plane + o);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) f[e] *= sc.v[e];
+    }
+}
+template <typename T, int VEC>
+PYTVB_HD void scale_by(T* v, const T* ts_plane, int o) {
+    if (ts_plane) {
+        const Pack<T, VEC> sc = ld_pack<T, VEC>(ts_plane + o);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) v[e] *= sc.v[e];
+    }
 }
 
 // Raw differences of one quad: d[k][e] = weight * (x[k+1] - x[k]) etc. WITHOUT the scheme's global divisor.
@@ -114,7 +136,7 @@ PYTVB_HD void strip_raw_diffs(T (*d)[VEC], const DualPlane<T, YT>& pl, const Par
     if (T_ON && C::NEED_BWD) ld_into<T, VEC>(tm, pl.tm + o);
     if (T_ON && C::NEED_FWD) ld_into<T, VEC>(tp, pl.tp + o);
     T fac[VEC];
-    if (T_ON) static_factor<T, VEC>(fac, P, i, j0);
+    if (T_ON) time_factor<T, VEC>(fac, P, pl.ts, i, j0, o);
     // centred scheme: in-plane factors (rows: uniform per row; columns: only the volume's first / last column)
     const T fi = (SCHEME == CENTRAL) ? ((i > 0 && i < P.Ni - 1) ? T(1) : T(0)) : T(1);
 #pragma unroll
@@ -232,6 +254,7 @@ struct PrimalPlane {
     const YT* tb_p;    // backward-type t component at plane t+1
     T az, bz, at, bt;  // weights * existence factors of the minus / plus z and t terms (see adjoint rule below)
     long long img;     // offset of image plane (z, t) in x / xbar / x0
+    const T* ts_m; const T* ts_c; const T* ts_p;   // per-voxel time scale at planes t-1, t, t+1 (clamped), or null
 };
 
 // Adjoint rule per axis (tv_operators_CPU.py:555-560, :488-493, :623-628), k = index along the axis:
@@ -256,6 +279,12 @@ PYTVB_HD PrimalPlane<T, YT> make_primal_plane(const FieldView<YT>& Y, const Para
     p.img = (long long)z * P.sZ + (long long)t * P.sT;
     p.zf_m = p.zb_p = p.tf_m = p.tb_p = p.y;
     p.az = p.bz = p.at = p.bt = T(0);
+    p.ts_m = p.ts_c = p.ts_p = nullptr;
+    if (T_ON && P.tscale) {
+        p.ts_c = P.tscale + p.img;
+        p.ts_m = t > 0 ? p.ts_c - P.sT : p.ts_c;
+        p.ts_p = t < P.M - 1 ? p.ts_c + P.sT : p.ts_c;
+    }
     if (Z_ON) {
         const long long zg = P.zg0 + z;
         T a, b;
@@ -388,6 +417,10 @@ PYTVB_HD void strip_quad_DT(T* out, const PrimalPlane<T, YT>& pl, const Params<T
         if (up_form && NF) ld_field<T, VEC, CG>(f_c, pl.y + (long long)C::T_F * P.sC + o); else zero_into<T, VEC>(f_c);
         if (!CTR && NB) ld_field<T, VEC, CG>(b_c, pl.y + (long long)C::T_B * P.sC + o); else zero_into<T, VEC>(b_c);
         if (NB && !(CTR && fb)) ld_field<T, VEC, CG>(b_p, pl.tb_p + o); else zero_into<T, VEC>(b_p);
+        if (pl.ts_c) {   // exact adjoint of the per-voxel time scale: every entry is scaled where it lives
+            scale_by<T, VEC>(f_m, pl.ts_m, o); scale_by<T, VEC>(f_c, pl.ts_c, o);
+            scale_by<T, VEC>(b_c, pl.ts_c, o); scale_by<T, VEC>(b_p, pl.ts_p, o);
+        }
         static_factor<T, VEC>(fac, P, i, j0);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
@@ -445,6 +478,7 @@ struct GradPlane {
     const T* w;  const T* wzm;  const T* wzp;  const T* wtm;  const T* wtp;    // inverse-norm planes, clamped
     T az, bz, at, bt;      // centred scheme: weight * existence of the minus / plus term; other schemes: weight
     bool z_fb, t_fb;       // centred scheme on a length-2 axis -> forward rule
+    const T* ts_m; const T* ts_c; const T* ts_p;   // per-voxel time scale at planes t-1, t, t+1 (clamped), or null
 };
 
 template <typename T, int SCHEME>
@@ -463,6 +497,12 @@ PYTVB_HD GradPlane<T> make_grad_plane(const ImgView<T>& X, const ImgView<T>& W, 
     g.at = g.bt = P.srt;
     g.z_fb = P.z_fwd_fallback != 0;
     g.t_fb = P.t_fwd_fallback != 0;
+    g.ts_m = g.ts_c = g.ts_p = nullptr;
+    if (P.tscale) {
+        g.ts_c = P.tscale + (long long)z * P.sZ + (long long)t * P.sT;
+        g.ts_m = v_tm ? g.ts_c - P.sT : g.ts_c;
+        g.ts_p = v_tp ? g.ts_c + P.sT : g.ts_c;
+    }
     if (SCHEME == CENTRAL) {
         if (!g.z_fb) {
             if (zg >= 2) g.xzm2 = X.row(P, z - 2, t, 0); else g.az = T(0);
@@ -541,9 +581,15 @@ PYTVB_HD void strip_quad_G(T* g_plane, const GradPlane<T>& pl, const Params<T>& 
         ld_into<T, VEC>(wm, pl.wtm + o);  ld_into<T, VEC>(wp, pl.wtp + o);
         if (CEN) { ld_into<T, VEC>(xm2, pl.xtm2 + o); ld_into<T, VEC>(xp2, pl.xtp2 + o); }
         static_factor<T, VEC>(fac, P, i, j0);
+        T wc[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) wc[e] = wr[e + 1];
+        if (pl.ts_c) {   // q = D w with D scaled where it lives: along t the inverse norms travel with their voxel's scale
+            scale_by<T, VEC>(wm, pl.ts_m, o); scale_by<T, VEC>(wc, pl.ts_c, o); scale_by<T, VEC>(wp, pl.ts_p, o);
+        }
 #pragma unroll
         for (int e = 0; e < VEC; ++e) {
-            const T v = strip_g_axis<T, SCHEME>(pl.t_fb, pl.at, pl.bt, CEN ? xm2[e] : T(0), xm[e], xr[e + 2], xp[e], CEN ? xp2[e] : T(0), wm[e], wr[e + 1], wp[e]);
+            const T v = strip_g_axis<T, SCHEME>(pl.t_fb, pl.at, pl.bt, CEN ? xm2[e] : T(0), xm[e], xr[e + 2], xp[e], CEN ? xp2[e] : T(0), wm[e], wc[e], wp[e]);
             g[e] += ((CEN && !pl.t_fb) ? v : P.srt * v) * fac[e];
         }
     }

@@ -126,6 +126,7 @@ extern "C" int pytvb_tv(const pytvb_problem* pb, const void* x, void* G, void* n
                         const void* halo_hi2, void* ws_reduce, void* ws_tv, void* stream) {
     if (int rc = check_problem(pb)) return rc;
     PYTVB_REQUIRE(x && G && d_tv && ws_reduce && ws_tv, "x, G, d_tv and the workspaces must not be NULL");
+    PYTVB_REQUIRE(!(pb->time_scale && (halo_lo2 || halo_hi2)), "time_scale is not available for slabs with z halos in pytvb_tv");
     if (axes_of(pb).z_on) {
         PYTVB_REQUIRE(!(pb->z_offset > 0 && !halo_lo2), "slab starts inside the volume: halo_lo2 (2 planes) is required");
         PYTVB_REQUIRE(!(pb->z_offset + pb->Nz < pb->Nz_global && !halo_hi2), "slab ends inside the volume: halo_hi2 (2 planes) is required");

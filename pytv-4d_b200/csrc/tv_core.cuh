@@ -67,6 +67,7 @@ struct Params {
     T srz, srt, sfac;             // sqrt(reg_z_over_reg), sqrt(reg_time), sqrt(factor_reg_static)
     T div, inv_div;               // global divisor: sqrt(2) hybrid, 2 central, 1 otherwise
     const uint8_t* mask_static;   // (Ni, Nj) bytes, nonzero = static pixel; or null
+    const T* tscale;              // (Nz, M, Ni, Nj) per-voxel factor of the time component(s) (sqrt of a weight map); or null
     long long sT, sZ;             // image strides (elements): Ni*Nj, M*Ni*Nj
     long long sC, sZf;            // field strides: component = M*Ni*Nj, plane group = Nd*M*Ni*Nj
 };

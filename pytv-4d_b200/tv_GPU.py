@@ -32,12 +32,13 @@ def _mask_to_device(mask, shape):
     return torch.broadcast_to(m, shape).to(torch.uint8).cuda().contiguous(), 0
 
 
-def _tv(scheme, img, mask, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor, return_grad_norms):
+def _tv(scheme, img, mask, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor, return_grad_norms, time_weight=None):
     shape = _dev.image_shape(img)
     x, was_tensor = _dev.to_device(img)
     lib = _lib.lib()
     ms = _dev.mask_static_to_device(mask_static, shape[2], shape[3])
-    pb = _dev.problem(scheme, x, shape, reg_z_over_reg, reg_time, factor_reg_static, ms)
+    ts = _dev.time_scale_to_device(time_weight, shape, x)
+    pb = _dev.problem(scheme, x, shape, reg_z_over_reg, reg_time, factor_reg_static, ms, ts=ts)
     st = _dev.stream_ptr()
     if _has_mask(mask):
         m, is_plane = _mask_to_device(mask, shape)
@@ -63,24 +64,24 @@ def _tv(scheme, img, mask, reg_z_over_reg, reg_time, mask_static, factor_reg_sta
 
 
 def tv_hybrid(img, mask=[], reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_reg_static=0, return_pytorch_tensor=False,
-              return_grad_norms=False):
+              return_grad_norms=False, time_weight=None):
     """TV value and sub-gradient, hybrid discretisation (tv_GPU.py:47)."""
-    return _tv("hybrid", img, mask, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor, return_grad_norms)
+    return _tv("hybrid", img, mask, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor, return_grad_norms, time_weight)
 
 
 def tv_downwind(img, mask=[], reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_reg_static=0, return_pytorch_tensor=False,
-                return_grad_norms=False):
+                return_grad_norms=False, time_weight=None):
     """TV value and sub-gradient, downwind discretisation (tv_GPU.py:142)."""
-    return _tv("downwind", img, mask, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor, return_grad_norms)
+    return _tv("downwind", img, mask, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor, return_grad_norms, time_weight)
 
 
 def tv_upwind(img, mask=[], reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_reg_static=0, return_pytorch_tensor=False,
-              return_grad_norms=False):
+              return_grad_norms=False, time_weight=None):
     """TV value and sub-gradient, upwind discretisation (tv_GPU.py:217)."""
-    return _tv("upwind", img, mask, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor, return_grad_norms)
+    return _tv("upwind", img, mask, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor, return_grad_norms, time_weight)
 
 
 def tv_central(img, mask=[], reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_reg_static=0, return_pytorch_tensor=False,
-               return_grad_norms=False):
+               return_grad_norms=False, time_weight=None):
     """TV value and sub-gradient, central discretisation (tv_GPU.py:290)."""
-    return _tv("central", img, mask, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor, return_grad_norms)
+    return _tv("central", img, mask, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor, return_grad_norms, time_weight)

@@ -7,6 +7,8 @@ Return conventions kept from the reference:
   * float32 stays float32, every other dtype is computed in float64 (`type_like`, :92-131);
   * compute_L21_norm returns a 0-d numpy array, and with return_array=True the norm array is a CUDA tensor
     even when return_pytorch_tensor=False (:83-90).
+Extension: every operator also takes `time_weight=None`, a (Nz, M, N, N) weight map of the time regularisation (the
+reference's TODO, README.md:258); mask_static / factor_reg_static keep working and multiply on top of it.
 Deliberate differences: outputs are allocated on the device (the reference allocates zeros on the host
 and uploads them, :175); float32 numpy input gives float32 output also for hybrid/central (the reference
 upcasts by accident under numpy >= 2); Ni != Nj is accepted.
@@ -49,25 +51,31 @@ def type_like(array, array_ref):
     return array.type(torch.float32 if ref_is_f32 else torch.float64)
 
 
-def _forward(scheme, img, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor):
+def _forward(scheme, img, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor, time_weight=None):
     shape = _dev.image_shape(img)
     x, was_tensor = _dev.to_device(img)
     ms = _dev.mask_static_to_device(mask_static, shape[2], shape[3])
-    pb = _dev.problem(scheme, x, shape, reg_z_over_reg, reg_time, factor_reg_static, ms)
+    ts = _dev.time_scale_to_device(time_weight, shape, x)
+    pb = _dev.problem(scheme, x, shape, reg_z_over_reg, reg_time, factor_reg_static, ms, ts=ts)
     Nd = _lib.lib().pytvb_num_components(ctypes.byref(pb))
+    if Nd < 0:
+        _lib.check(Nd)
     out = torch.empty((shape[0], Nd) + shape[1:], dtype=x.dtype, device=x.device)
     _lib.check(_lib.lib().pytvb_D(ctypes.byref(pb), _dev.ptr(x), _dev.ptr(out), None, None, _dev.stream_ptr()))
     return _dev.to_output(out, return_pytorch_tensor or was_tensor)
 
 
-def _adjoint(scheme, field, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor):
+def _adjoint(scheme, field, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor, time_weight=None):
     if field.ndim != 5:
         raise IndexError("D_T expects a 5-D field (Nz, Nd, M, N, N); got %d dimensions" % field.ndim)
     p, was_tensor = _dev.to_device(field)
     Nz, Nd, M, Ni, Nj = (int(s) for s in p.shape)
     ms = _dev.mask_static_to_device(mask_static, Ni, Nj)
-    pb = _dev.problem(scheme, p, (Nz, M, Ni, Nj), reg_z_over_reg, reg_time, factor_reg_static, ms)
+    ts = _dev.time_scale_to_device(time_weight, (Nz, M, Ni, Nj), p)
+    pb = _dev.problem(scheme, p, (Nz, M, Ni, Nj), reg_z_over_reg, reg_time, factor_reg_static, ms, ts=ts)
     expect = _lib.lib().pytvb_num_components(ctypes.byref(pb))
+    if expect < 0:
+        _lib.check(expect)
     if expect != Nd:
         raise IndexError("field has %d components but D_T_%s with these weights acts on %d" % (Nd, scheme, expect))
     out = torch.empty((Nz, M, Ni, Nj), dtype=p.dtype, device=p.device)
@@ -75,41 +83,41 @@ def _adjoint(scheme, field, reg_z_over_reg, reg_time, mask_static, factor_reg_st
     return _dev.to_output(out, return_pytorch_tensor or was_tensor)
 
 
-def D_hybrid(img, reg_z_over_reg=1.0, reg_time=0, mask_static=False, factor_reg_static=0, return_pytorch_tensor=False):
+def D_hybrid(img, reg_z_over_reg=1.0, reg_time=0, mask_static=False, factor_reg_static=0, return_pytorch_tensor=False, time_weight=None):
     """(Nz,M,N,N) -> (Nz,Nd,M,N,N), hybrid scheme, Nd = 4/6/8 (tv_operators_GPU.py:134)."""
-    return _forward("hybrid", img, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor)
+    return _forward("hybrid", img, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor, time_weight)
 
 
-def D_downwind(img, reg_z_over_reg=1.0, reg_time=0, mask_static=False, factor_reg_static=0, return_pytorch_tensor=False):
+def D_downwind(img, reg_z_over_reg=1.0, reg_time=0, mask_static=False, factor_reg_static=0, return_pytorch_tensor=False, time_weight=None):
     """Backward differences, Nd = 2/3/4 (tv_operators_GPU.py:253)."""
-    return _forward("downwind", img, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor)
+    return _forward("downwind", img, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor, time_weight)
 
 
-def D_upwind(img, reg_z_over_reg=1.0, reg_time=0, mask_static=False, factor_reg_static=0, return_pytorch_tensor=False):
+def D_upwind(img, reg_z_over_reg=1.0, reg_time=0, mask_static=False, factor_reg_static=0, return_pytorch_tensor=False, time_weight=None):
     """Forward differences, Nd = 2/3/4 (tv_operators_GPU.py:362)."""
-    return _forward("upwind", img, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor)
+    return _forward("upwind", img, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor, time_weight)
 
 
-def D_central(img, reg_z_over_reg=1.0, reg_time=0, mask_static=False, factor_reg_static=0, return_pytorch_tensor=False):
+def D_central(img, reg_z_over_reg=1.0, reg_time=0, mask_static=False, factor_reg_static=0, return_pytorch_tensor=False, time_weight=None):
     """Centred differences / 2, Nd = 2/3/4 (tv_operators_GPU.py:471)."""
-    return _forward("central", img, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor)
+    return _forward("central", img, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor, time_weight)
 
 
-def D_T_hybrid(img, reg_z_over_reg=1.0, reg_time=0, mask_static=False, factor_reg_static=0, return_pytorch_tensor=False):
+def D_T_hybrid(img, reg_z_over_reg=1.0, reg_time=0, mask_static=False, factor_reg_static=0, return_pytorch_tensor=False, time_weight=None):
     """(Nz,Nd,M,N,N) -> (Nz,M,N,N), adjoint of D_hybrid (tv_operators_GPU.py:583)."""
-    return _adjoint("hybrid", img, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor)
+    return _adjoint("hybrid", img, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor, time_weight)
 
 
-def D_T_downwind(img, reg_z_over_reg=1.0, reg_time=0, mask_static=False, factor_reg_static=0, return_pytorch_tensor=False):
+def D_T_downwind(img, reg_z_over_reg=1.0, reg_time=0, mask_static=False, factor_reg_static=0, return_pytorch_tensor=False, time_weight=None):
     """Adjoint of D_downwind (tv_operators_GPU.py:719)."""
-    return _adjoint("downwind", img, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor)
+    return _adjoint("downwind", img, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor, time_weight)
 
 
-def D_T_upwind(img, reg_z_over_reg=1.0, reg_time=0, mask_static=False, factor_reg_static=0, return_pytorch_tensor=False):
+def D_T_upwind(img, reg_z_over_reg=1.0, reg_time=0, mask_static=False, factor_reg_static=0, return_pytorch_tensor=False, time_weight=None):
     """Adjoint of D_upwind (tv_operators_GPU.py:828)."""
-    return _adjoint("upwind", img, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor)
+    return _adjoint("upwind", img, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor, time_weight)
 
 
-def D_T_central(img, reg_z_over_reg=1.0, reg_time=0, mask_static=False, factor_reg_static=0, return_pytorch_tensor=False):
+def D_T_central(img, reg_z_over_reg=1.0, reg_time=0, mask_static=False, factor_reg_static=0, return_pytorch_tensor=False, time_weight=None):
     """Adjoint of D_central (tv_operators_GPU.py:938); no Nz >= 5 / N >= 5 restriction."""
-    return _adjoint("central", img, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor)
+    return _adjoint("central", img, reg_z_over_reg, reg_time, mask_static, factor_reg_static, return_pytorch_tensor, time_weight)

@@ -45,13 +45,16 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
-def _problem(scheme, x_dtype, shape, rz, rt, mask_static, fac, z_offset=0, Nz_global=None):
+def _problem(scheme, x_dtype, shape, rz, rt, mask_static, fac, z_offset=0, Nz_global=None, time_weight=None):
     ms = None
     if not isinstance(mask_static, bool) and mask_static is not None:
         ms = np.ascontiguousarray(np.asarray(mask_static).reshape(shape[-2], shape[-1]).astype(np.uint8))
+    ts = None
+    if time_weight is not None:
+        ts = np.ascontiguousarray(np.sqrt(np.broadcast_to(np.asarray(time_weight, dtype=np.float64), shape)).astype(x_dtype))
     pb = _lib.make_problem(scheme, _lib.F32 if x_dtype == np.float32 else _lib.F64, shape, rz, rt, fac,
-                           ms.ctypes.data if ms is not None else None, z_offset, Nz_global)
-    return pb, ms
+                           ms.ctypes.data if ms is not None else None, z_offset, Nz_global, ts.ctypes.data if ts is not None else None)
+    return pb, (ms, ts)
 
 
 def _call(op, pb, inp, out, out2=None, aux=None, x0=None, lo=None, hi=None, c0=0.0, c1=0.0, variant=0, scalar=False):
@@ -69,19 +72,19 @@ def nd_of(pb):
 
 
 def D(x, scheme, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_reg_static=0.0, lo=None, hi=None, z_offset=0, Nz_global=None,
-      scalar=False):
+      scalar=False, time_weight=None):
     x = np.ascontiguousarray(x)
-    pb, keep = _problem(scheme, x.dtype, x.shape, reg_z_over_reg, reg_time, mask_static, factor_reg_static, z_offset, Nz_global)
+    pb, keep = _problem(scheme, x.dtype, x.shape, reg_z_over_reg, reg_time, mask_static, factor_reg_static, z_offset, Nz_global, time_weight)
     out = np.full((x.shape[0], nd_of(pb)) + x.shape[1:], np.nan, dtype=x.dtype)
     _call(0 if GEN == 1 else 7, pb, x, out, lo=lo, hi=hi, scalar=scalar)
     return out
 
 
 def D_T(p, scheme, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_reg_static=0.0, lo=None, hi=None, z_offset=0, Nz_global=None,
-        scalar=False):
+        scalar=False, time_weight=None):
     p = np.ascontiguousarray(p)
     shape = (p.shape[0],) + p.shape[2:]
-    pb, keep = _problem(scheme, p.dtype, shape, reg_z_over_reg, reg_time, mask_static, factor_reg_static, z_offset, Nz_global)
+    pb, keep = _problem(scheme, p.dtype, shape, reg_z_over_reg, reg_time, mask_static, factor_reg_static, z_offset, Nz_global, time_weight)
     assert nd_of(pb) == p.shape[1]
     out = np.full(shape, np.nan, dtype=p.dtype)
     _call(1 if GEN == 1 else 8, pb, p, out, lo=lo, hi=hi, scalar=scalar)
@@ -89,9 +92,9 @@ def D_T(p, scheme, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_r
 
 
 def tv(x, scheme, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_reg_static=0.0, lo=None, hi=None, z_offset=0, Nz_global=None,
-       scalar=False):
+       scalar=False, time_weight=None):
     x = np.ascontiguousarray(x)
-    pb, keep = _problem(scheme, x.dtype, x.shape, reg_z_over_reg, reg_time, mask_static, factor_reg_static, z_offset, Nz_global)
+    pb, keep = _problem(scheme, x.dtype, x.shape, reg_z_over_reg, reg_time, mask_static, factor_reg_static, z_offset, Nz_global, time_weight)
     G = np.full(x.shape, np.nan, dtype=x.dtype)
     norms = np.full(x.shape, np.nan, dtype=x.dtype)
     val = _call(2 if GEN == 1 else 9, pb, x, G, out2=norms, lo=lo, hi=hi, scalar=scalar)
@@ -100,13 +103,13 @@ def tv(x, scheme, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_re
 
 def cp_dual(xbar, y, scheme, lam, sigma, lo=None, hi=None, z_offset=0, Nz_global=None, scalar=False, **w):
     pb, keep = _problem(scheme, xbar.dtype, xbar.shape, w.get("reg_z_over_reg", 1.0), w.get("reg_time", 0.0), w.get("mask_static", False),
-                        w.get("factor_reg_static", 0.0), z_offset, Nz_global)
+                        w.get("factor_reg_static", 0.0), z_offset, Nz_global, w.get("time_weight"))
     return _call(3 if GEN == 1 else 5, pb, np.ascontiguousarray(xbar), y, lo=lo, hi=hi, c0=sigma, c1=1.0 / lam, scalar=scalar)
 
 
 def cp_primal(y, x, aux, x0, scheme, tau, c2, variant, lo=None, hi=None, z_offset=0, Nz_global=None, scalar=False, **w):
     pb, keep = _problem(scheme, x.dtype, x.shape, w.get("reg_z_over_reg", 1.0), w.get("reg_time", 0.0), w.get("mask_static", False),
-                        w.get("factor_reg_static", 0.0), z_offset, Nz_global)
+                        w.get("factor_reg_static", 0.0), z_offset, Nz_global, w.get("time_weight"))
     return _call(4 if GEN == 1 else 6, pb, np.ascontiguousarray(y), x, aux=aux, x0=x0, lo=lo, hi=hi, c0=tau, c1=c2, variant=variant, scalar=scalar)
 
 

@@ -30,9 +30,10 @@ def test_header_symbols_are_exported_and_bound():
 
 
 def test_problem_struct_layout_matches_header():
-    # 2 x int32, 6 x int64, 3 x double, 1 pointer, no padding surprises
-    assert ctypes.sizeof(_lib.Problem) == 8 + 6 * 8 + 3 * 8 + 8
+    # 2 x int32, 6 x int64, 3 x double, 2 pointers, no padding surprises
+    assert ctypes.sizeof(_lib.Problem) == 8 + 6 * 8 + 3 * 8 + 2 * 8
     assert _lib.Problem.Nz.offset == 8 and _lib.Problem.reg_z_over_reg.offset == 56 and _lib.Problem.mask_static.offset == 80
+    assert _lib.Problem.time_scale.offset == 88
 
 
 @pytest.mark.parametrize("scheme,Nz,M,rz,rt,expect", [

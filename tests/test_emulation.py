@@ -294,3 +294,44 @@ def test_non_square_images(gen):
         tvo, Go = orc.tv(x.copy(), scheme, **kw)
         assert tv == pytest.approx(tvo, rel=1e-13)
         np.testing.assert_allclose(G, Go, atol=1e-12)
+
+
+# ------------------------------------------------------------------ extension: per-voxel weight map of the time axis
+@pytest.mark.parametrize("scalar", [False, True], ids=["vec", "scalar"])
+@pytest.mark.parametrize("shape", [(3, 4, 6, 8), (1, 2, 5, 4), (4, 3, 7, 12), (2, 5, 3, 8)], ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_time_weight_map(scheme, shape, scalar):
+    """Strip kernels with a (Nz,M,N,N) weight map of the time regularisation (+ mask_static on top) against the oracle:
+    D, exact adjoint, TV / sub-gradient, and one CP iteration of both forms."""
+    old = em.GEN
+    em.GEN = 2
+    try:
+        rs = np.random.RandomState(19)
+        Nz, M, Ni, Nj = shape
+        x = rs.rand(*shape)
+        W = rs.rand(*shape) * 3
+        ms = rs.rand(1, 1, Ni, Nj) > 0.5
+        kw = dict(reg_z_over_reg=0.6, reg_time=0.4, mask_static=ms, factor_reg_static=2.0, time_weight=W)
+        D_o = orc.D(x, scheme, **kw)
+        np.testing.assert_allclose(em.D(x, scheme, scalar=scalar, **kw), D_o, atol=1e-14)
+        p = rs.randn(*D_o.shape)
+        np.testing.assert_allclose(em.D_T(p, scheme, scalar=scalar, **kw), orc.D_T(p, scheme, **kw), atol=1e-13)
+        tv, G, n = em.tv(x, scheme, scalar=scalar, **kw)
+        tv_o, G_o, n_o = orc.tv(x.copy(), scheme, return_grad_norms=True, **kw)
+        assert tv == pytest.approx(tv_o, rel=1e-13)
+        np.testing.assert_allclose(G, G_o, atol=1e-12)
+        np.testing.assert_allclose(n, n_o, atol=1e-13)
+        Nd = D_o.shape[1]
+        y = 0.2 * rs.randn(Nz, Nd, M, Ni, Nj)
+        xx = x + 0.1 * rs.randn(*shape)
+        xbar = xx + 0.01 * rs.randn(*shape)
+        x_ref, xb_ref, y_ref, e_ref = orc.cp_rof_step(xx.copy(), xbar.copy(), x, y.copy(), scheme, lam=0.1, sigma=0.5, tau=0.07, theta=0.9, **kw)
+        yy, x2, aux = y.copy(), xx.copy(), xbar.copy()
+        l21 = em.cp_dual(xbar, yy, scheme, 0.1, 0.5, scalar=scalar, **kw)
+        fid = em.cp_primal(yy, x2, aux, x, scheme, 0.07, 0.9, 0, scalar=scalar, **kw)
+        np.testing.assert_allclose(yy, y_ref, atol=1e-13)
+        np.testing.assert_allclose(x2, x_ref, atol=1e-13)
+        np.testing.assert_allclose(aux, xb_ref, atol=1e-13)
+        assert 0.5 * fid + 0.1 * l21 == pytest.approx(e_ref, rel=1e-12)
+    finally:
+        em.GEN = old

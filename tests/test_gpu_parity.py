@@ -333,6 +333,50 @@ def test_odd_and_multi_block_shapes(scheme, shape):
     assert s.energy() == pytest.approx(e, rel=1e-12)
 
 
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_time_weight_map(scheme, golden_small):
+    """Extension (reference TODO, README.md:258): a (Nz,M,N,N) weight map of the time regularisation.  (1) the map
+    where(mask, factor, 1) reproduces the reference's mask_static goldens; (2) a random map (with mask_static on top)
+    matches the oracle for D, D_T, tv and CP, in float64 and float32; (3) adjointness."""
+    import os
+    if os.environ.get("PYTVB_GEN") == "1":
+        with pytest.raises(_lib.PytvError, match="generation-2"):
+            D_(scheme)(np.zeros((2, 2, 4, 4)), reg_time=1.0, time_weight=np.ones((2, 2, 4, 4)))
+        return
+    case = [c for c in cases.small_cases() if c["key"] == "4x3x8/ztmask/" + scheme][0]
+    x = cases.make_image(case)
+    W = np.broadcast_to(np.where(cases.make_mask_static(case), case["fac"], 1.0), x.shape)
+    kw = dict(reg_z_over_reg=case["rz"], reg_time=case["rt"], time_weight=W)
+    np.testing.assert_allclose(D_(scheme)(x, **kw), golden_small[case["key"] + "/D"], atol=1e-13)
+    tv, G = tv_(scheme)(x.copy(), **kw)
+    assert float(tv) == pytest.approx(float(golden_small[case["key"] + "/tv"]), rel=1e-13)
+    np.testing.assert_allclose(G, golden_small[case["key"] + "/G"], atol=1e-10)
+    rs = np.random.RandomState(19)
+    shape = (4, 5, 33, 68)
+    x = rs.rand(*shape)
+    W = rs.rand(*shape) * 3
+    kw = dict(reg_z_over_reg=0.6, reg_time=0.4, mask_static=rs.rand(1, 1, 33, 68) > 0.5, factor_reg_static=2.0, time_weight=W)
+    D_o = orc.D(x, scheme, **kw)
+    Dx = D_(scheme)(x, **kw)
+    np.testing.assert_allclose(Dx, D_o, atol=1e-14)
+    p = rs.randn(*D_o.shape)
+    DTp = DT_(scheme)(p, **kw)
+    np.testing.assert_allclose(DTp, orc.D_T(p, scheme, **kw), atol=1e-12)
+    assert np.sum(Dx * p) == pytest.approx(np.sum(x * DTp), rel=1e-12)
+    tv, G, n = tv_(scheme)(x.copy(), return_grad_norms=True, **kw)
+    tv_o, G_o, n_o = orc.tv(x.copy(), scheme, return_grad_norms=True, **kw)
+    assert float(tv) == pytest.approx(tv_o, rel=1e-13)
+    np.testing.assert_allclose(G, G_o, atol=1e-10)
+    np.testing.assert_allclose(Dx.astype(np.float32), D_(scheme)(x.astype(np.float32), **kw), atol=1e-5)
+    s = pytv.CPSolver(x, lam=0.1, scheme=scheme, variant="rof", sigma=0.5, tau=0.07, **kw)
+    s.step(3)
+    xo, xb, y = x.copy(), x.copy(), np.zeros_like(D_o)
+    for _ in range(3):
+        xo, xb, y, e = orc.cp_rof_step(xo, xb, x, y, scheme, lam=0.1, sigma=0.5, tau=0.07, theta=1.0, **kw)
+    np.testing.assert_allclose(s.x.cpu().numpy(), xo, atol=1e-12)
+    assert s.energy() == pytest.approx(e, rel=1e-12)
+
+
 # ------------------------------------------------------------------ Chambolle-Pock
 @pytest.mark.parametrize("shape", [(3, 2, 5, 8), (2, 3, 6, 4), (1, 1, 7, 12), (5, 1, 4, 8), (1, 4, 3, 4), (2, 2, 1, 4), (3, 3, 2, 8), (4, 2, 33, 260)],
                          ids=lambda s: "x".join(map(str, s)))
