@@ -34,7 +34,7 @@ inline Tiling make_strip_tiling(int Nj, int Ni, int M, int nz, int vec, int z_lo
     return t;
 }
 
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, typename YT = T>
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, typename YT = T, bool TS = false>
 __global__ void __launch_bounds__(CTA_THREADS, PYTVB_DUAL_MINB) cp_dual_strip_kernel(ImgView<T> Xb, YT* __restrict__ y, double* __restrict__ partial, Params<T> P, T sig,
                                                                     T lam, Tiling tl) {
     const QuadIdx q = decode_quad(tl, (P.Ni + R - 1) / R, VEC);   // q.i = strip index
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(CTA_THREADS, PYTVB_DUAL_MINB) cp_dual_strip_ke
                 const int o = i * P.Nj + q.j0;
                 const int o_up = i > 0 ? o - P.Nj : o;
                 const int o_dn = i < P.Ni - 1 ? o + P.Nj : o;
-                l21 += strip_quad_cp_dual<T, VEC, SCHEME, Z_ON, T_ON, YT>(pl, P, i, q.j0, o, o_up, o_dn, sig, lam);
+                l21 += strip_quad_cp_dual<T, VEC, SCHEME, Z_ON, T_ON, YT, TS>(pl, P, i, q.j0, o, o_up, o_dn, sig, lam);
             }
         }
     }
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(CTA_THREADS, PYTVB_DUAL_MINB) cp_dual_strip_ke
     }
 }
 
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int VARIANT, int R, typename YT = T>
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int VARIANT, int R, typename YT = T, bool TS = false>
 __global__ void __launch_bounds__(CTA_THREADS, PYTVB_PRIMAL_MINB) cp_primal_strip_kernel(FieldView<YT> Y, T* __restrict__ x, T* __restrict__ aux, const T* __restrict__ x0,
                                                                       double* __restrict__ partial, Params<T> P, T tau, T c1, T c2, Tiling tl, T tau_x0 = T(-1)) {
     const QuadIdx q = decode_quad(tl, (P.Ni + R - 1) / R, VEC);
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(CTA_THREADS, PYTVB_PRIMAL_MINB) cp_primal_stri
                 const int o = i * P.Nj + q.j0;
                 const int o_up = i > 0 ? o - P.Nj : o;
                 const int o_dn = i < P.Ni - 1 ? o + P.Nj : o;
-                fid += strip_quad_cp_primal<T, VEC, SCHEME, Z_ON, T_ON, VARIANT, false, YT>(x, aux, x0, pl, P, i, q.j0, o, o_up, o_dn, tau, c1, c2, tau_x0);
+                fid += strip_quad_cp_primal<T, VEC, SCHEME, Z_ON, T_ON, VARIANT, false, YT, TS>(x, aux, x0, pl, P, i, q.j0, o, o_up, o_dn, tau, c1, c2, tau_x0);
             }
         }
     }
@@ -98,24 +98,24 @@ __device__ __forceinline__ void for_strip_rows(const QuadIdx& q, int Ni, int Nj,
     }
 }
 
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R>
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, bool TS = false>
 __global__ void __launch_bounds__(CTA_THREADS) D_strip_kernel(ImgView<T> X, T* __restrict__ D, Params<T> P, Tiling tl) {
     const QuadIdx q = decode_quad(tl, (P.Ni + R - 1) / R, VEC);
     if (!q.active) return;
     const DualPlane<T> pl = make_dual_plane<T, SCHEME>(X, D, P, q.z, q.t);   // pl.y = component 0 of D at plane (z, t)
     for_strip_rows<R>(q, P.Ni, P.Nj, [&](int i, int o, int o_up, int o_dn) {
-        strip_quad_D<T, VEC, SCHEME, Z_ON, T_ON>(pl.y, pl, P, i, q.j0, o, o_up, o_dn);
+        strip_quad_D<T, VEC, SCHEME, Z_ON, T_ON, TS>(pl.y, pl, P, i, q.j0, o, o_up, o_dn);
     });
 }
 
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R>
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, bool TS = false>
 __global__ void __launch_bounds__(CTA_THREADS) DT_strip_kernel(FieldView<T> Pf, T* __restrict__ out, Params<T> P, Tiling tl) {
     const QuadIdx q = decode_quad(tl, (P.Ni + R - 1) / R, VEC);
     if (!q.active) return;
     const PrimalPlane<T> pl = make_primal_plane<T, SCHEME, Z_ON, T_ON>(Pf, P, q.z, q.t);
     for_strip_rows<R>(q, P.Ni, P.Nj, [&](int i, int o, int o_up, int o_dn) {
         T v[VEC];
-        strip_quad_DT<T, VEC, SCHEME, Z_ON, T_ON>(v, pl, P, i, q.j0, o, o_up, o_dn);
+        strip_quad_DT<T, VEC, SCHEME, Z_ON, T_ON, false, T, TS>(v, pl, P, i, q.j0, o, o_up, o_dn);
         Pack<T, VEC> pk;
 #pragma unroll
         for (int e = 0; e < VEC; ++e) pk.v[e] = v[e];
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(CTA_THREADS) l21_strip_kernel(const T* __restr
 }
 
 // TV sweep 1 (strip form): z range tl.z_lo .. tl.z_lo+tl.nz-1 includes one halo plane per side when present.
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R>
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, bool TS = false>
 __global__ void __launch_bounds__(CTA_THREADS) tv_norm_strip_kernel(ImgView<T> X, T* __restrict__ Wz0, T* __restrict__ norms, double* __restrict__ partial,
                                                                     Params<T> P, Tiling tl) {
     const QuadIdx q = decode_quad(tl, (P.Ni + R - 1) / R, VEC);
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(CTA_THREADS) tv_norm_strip_kernel(ImgView<T> X
         const bool own = q.z >= 0 && q.z < P.Nz;
         T* np = (norms && own) ? norms + img : nullptr;
         for_strip_rows<R>(q, P.Ni, P.Nj, [&](int i, int o, int o_up, int o_dn) {
-            const T v = strip_quad_tv_norm<T, VEC, SCHEME, Z_ON, T_ON>(Wz0 ? Wz0 + img : nullptr, np, pl, P, i, q.j0, o, o_up, o_dn);
+            const T v = strip_quad_tv_norm<T, VEC, SCHEME, Z_ON, T_ON, TS>(Wz0 ? Wz0 + img : nullptr, np, pl, P, i, q.j0, o, o_up, o_dn);
             if (own) sum += v;
         });
     }
@@ -173,13 +173,13 @@ __global__ void __launch_bounds__(CTA_THREADS) tv_norm_strip_kernel(ImgView<T> X
     if (threadIdx.x == 0) partial[blockIdx.x] = bs;
 }
 
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R>
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, bool TS = false>
 __global__ void __launch_bounds__(CTA_THREADS) tv_grad_strip_kernel(ImgView<T> X, ImgView<T> W, T* __restrict__ G, Params<T> P, Tiling tl) {
     const QuadIdx q = decode_quad(tl, (P.Ni + R - 1) / R, VEC);
     if (!q.active) return;
     const GradPlane<T> pl = make_grad_plane<T, SCHEME>(X, W, P, q.z, q.t);
     T* gp = G + (long long)q.z * P.sZ + (long long)q.t * P.sT;
-    for_strip_rows<R>(q, P.Ni, P.Nj, [&](int i, int o, int, int) { strip_quad_G<T, VEC, SCHEME, Z_ON, T_ON>(gp, pl, P, i, q.j0, o); });
+    for_strip_rows<R>(q, P.Ni, P.Nj, [&](int i, int o, int, int) { strip_quad_G<T, VEC, SCHEME, Z_ON, T_ON, TS>(gp, pl, P, i, q.j0, o); });
 }
 
 }  // namespace pytvb

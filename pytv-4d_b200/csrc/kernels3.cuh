@@ -117,7 +117,7 @@ static __global__ void fused_check_kernel(const unsigned* error, double* d_l21, 
 #ifndef PYTVB_FUSED_MINB
 #define PYTVB_FUSED_MINB PYTVB_DUAL_MINB
 #endif
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int VARIANT, int R>
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int VARIANT, int R, bool TS = false>
 __global__ void __launch_bounds__(CTA_THREADS, PYTVB_FUSED_MINB)
 cp_fused_kernel(ImgView<T> Xin, FieldView<T> Y, T* __restrict__ y, T* __restrict__ x, T* __restrict__ aux, const T* __restrict__ x0,
                 double* __restrict__ partialA, double* __restrict__ partialB, Params<T> P, T sig, T lam, T tau, T c1, T c2, FusedSched s, FusedCtl ctl) {
@@ -143,7 +143,7 @@ cp_fused_kernel(ImgView<T> Xin, FieldView<T> Y, T* __restrict__ y, T* __restrict
                 const int i = i0 + r;
                 if (i < P.Ni) {
                     const int o = i * P.Nj + j0;
-                    l21 += strip_quad_cp_dual<T, VEC, SCHEME, Z_ON, T_ON>(pl, P, i, j0, o, i > 0 ? o - P.Nj : o, i < P.Ni - 1 ? o + P.Nj : o, sig, lam);
+                    l21 += strip_quad_cp_dual<T, VEC, SCHEME, Z_ON, T_ON, T, TS>(pl, P, i, j0, o, i > 0 ? o - P.Nj : o, i < P.Ni - 1 ? o + P.Nj : o, sig, lam);
                 }
             }
         }
@@ -171,7 +171,7 @@ cp_fused_kernel(ImgView<T> Xin, FieldView<T> Y, T* __restrict__ y, T* __restrict
                 const int i = i0 + r;
                 if (r < nrows && i >= 0 && i < P.Ni) {
                     const int o = i * P.Nj + j0;
-                    fid += strip_quad_cp_primal<T, VEC, SCHEME, Z_ON, T_ON, VARIANT, true>(x, aux, x0, pl, P, i, j0, o, i > 0 ? o - P.Nj : o,
+                    fid += strip_quad_cp_primal<T, VEC, SCHEME, Z_ON, T_ON, VARIANT, true, T, TS>(x, aux, x0, pl, P, i, j0, o, i > 0 ? o - P.Nj : o,
                                                                                            i < P.Ni - 1 ? o + P.Nj : o, tau, c1, c2);
                 }
             }

@@ -25,7 +25,8 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchD {
                 constexpr int R = PYTVB_STRIP_R;
                 const Tiling tl = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.P.Nz, VEC);
                 if (int rc = check_grid(tl)) return rc;
-                D_strip_kernel<T, VEC, SCHEME, Z, TT, R><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.D, a.P, tl);
+                if (TT && a.P.tscale) D_strip_kernel<T, VEC, SCHEME, Z, TT, R, TT><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.D, a.P, tl);
+                else D_strip_kernel<T, VEC, SCHEME, Z, TT, R, false><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.D, a.P, tl);
                 count_launches(1);
                 PYTVB_CUDA(cudaGetLastError());
                 return PYTVB_OK;
@@ -48,7 +49,8 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchDT {
                 constexpr int R = PYTVB_STRIP_R;
                 const Tiling tl = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.P.Nz, VEC);
                 if (int rc = check_grid(tl)) return rc;
-                DT_strip_kernel<T, VEC, SCHEME, Z, TT, R><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.F, a.out, a.P, tl);
+                if (TT && a.P.tscale) DT_strip_kernel<T, VEC, SCHEME, Z, TT, R, TT><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.F, a.out, a.P, tl);
+                else DT_strip_kernel<T, VEC, SCHEME, Z, TT, R, false><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.F, a.out, a.P, tl);
                 count_launches(1);
                 PYTVB_CUDA(cudaGetLastError());
                 return PYTVB_OK;

@@ -122,8 +122,11 @@ PYTVB_HD void scale_by(T* v, const T* ts_plane, int o) {
 
 // Raw differences of one quad: d[k][e] = weight * (x[k+1] - x[k]) etc. WITHOUT the scheme's global divisor.
 // o = i*Nj + j0; o_up / o_dn = offsets of rows i-1 / i+1 clamped to [0, Ni).
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, typename YT = T>
-PYTVB_HD void strip_raw_diffs(T (*d)[VEC], const DualPlane<T, YT>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn) {
+// (TS = a per-voxel time scale is present.  It is a template parameter all the way up to the kernels: folding the null
+// checks into the common body cost pass B 12 %, and even two variants behind one uniform branch inside one kernel cost
+// 7 % (register pressure), so the no-weight-map kernels are kept bit-identical to what they were before the extension.)
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, typename YT, bool TS>
+PYTVB_HD void strip_raw_diffs_impl(T (*d)[VEC], const DualPlane<T, YT>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn) {
     typedef Comp<SCHEME, Z_ON, T_ON> C;
     T c[VEC + 2], up[VEC], dn[VEC], zm[VEC], zp[VEC], tm[VEC], tp[VEC];
     ld_into<T, VEC>(c + 1, pl.c + o);
@@ -136,7 +139,7 @@ PYTVB_HD void strip_raw_diffs(T (*d)[VEC], const DualPlane<T, YT>& pl, const Par
     if (T_ON && C::NEED_BWD) ld_into<T, VEC>(tm, pl.tm + o);
     if (T_ON && C::NEED_FWD) ld_into<T, VEC>(tp, pl.tp + o);
     T fac[VEC];
-    if (T_ON) time_factor<T, VEC>(fac, P, pl.ts, i, j0, o);
+    if (T_ON) { if constexpr (TS) time_factor<T, VEC>(fac, P, pl.ts, i, j0, o); else static_factor<T, VEC>(fac, P, i, j0); }
     // centred scheme: in-plane factors (rows: uniform per row; columns: only the volume's first / last column)
     const T fi = (SCHEME == CENTRAL) ? ((i > 0 && i < P.Ni - 1) ? T(1) : T(0)) : T(1);
 #pragma unroll
@@ -170,16 +173,21 @@ PYTVB_HD void strip_raw_diffs(T (*d)[VEC], const DualPlane<T, YT>& pl, const Par
     }
 }
 
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, typename YT = T, bool TS = false>
+PYTVB_HD void strip_raw_diffs(T (*d)[VEC], const DualPlane<T, YT>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn) {
+    strip_raw_diffs_impl<T, VEC, SCHEME, Z_ON, T_ON, YT, TS && T_ON>(d, pl, P, i, j0, o, o_up, o_dn);
+}
+
 // One quad of the dual pass.  sig = sigma * inv_div (so that y + sigma*D = y + sig*raw_difference).
 // Returns sum_e sqrt(sum_k raw_k^2) (the caller multiplies the total by inv_div to get L21(D xbar)).
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, typename YT = T>
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, typename YT = T, bool TS = false>
 PYTVB_HD T strip_quad_cp_dual(const DualPlane<T, YT>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn, T sig, T lam) {
     typedef Comp<SCHEME, Z_ON, T_ON> C;
     constexpr int ND = C::ND;
     T y[ND][VEC], d[ND][VEC];
 #pragma unroll
     for (int k = 0; k < ND; ++k) ld_y<T, YT, VEC>(y[k], pl.y + (long long)k * P.sC + o);
-    strip_raw_diffs<T, VEC, SCHEME, Z_ON, T_ON, YT>(d, pl, P, i, j0, o, o_up, o_dn);
+    strip_raw_diffs<T, VEC, SCHEME, Z_ON, T_ON, YT, TS>(d, pl, P, i, j0, o, o_up, o_dn);
     T l21 = T(0);
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
@@ -204,11 +212,11 @@ PYTVB_HD T strip_quad_cp_dual(const DualPlane<T, YT>& pl, const Params<T>& P, in
 }
 
 // D_scheme at one quad, stored to the field plane `out` (component 0 of plane (z,t); component k at + k*sC).
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON>
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, bool TS = false>
 PYTVB_HD void strip_quad_D(T* out, const DualPlane<T>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn) {
     typedef Comp<SCHEME, Z_ON, T_ON> C;
     T d[C::ND][VEC];
-    strip_raw_diffs<T, VEC, SCHEME, Z_ON, T_ON>(d, pl, P, i, j0, o, o_up, o_dn);
+    strip_raw_diffs<T, VEC, SCHEME, Z_ON, T_ON, T, TS>(d, pl, P, i, j0, o, o_up, o_dn);
 #pragma unroll
     for (int k = 0; k < C::ND; ++k) {
         Pack<T, VEC> pk;
@@ -220,11 +228,11 @@ PYTVB_HD void strip_quad_D(T* out, const DualPlane<T>& pl, const Params<T>& P, i
 
 // TV sweep 1 at one quad: w = 1/|D x| (0 where the norm is 0) into `w_plane`, optional norms (inf where 0)
 // into `n_plane`; returns the sum of the norms.  |D x| = inv_div * sqrt(sum raw^2).
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON>
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, bool TS = false>
 PYTVB_HD T strip_quad_tv_norm(T* w_plane, T* n_plane, const DualPlane<T>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn) {
     typedef Comp<SCHEME, Z_ON, T_ON> C;
     T d[C::ND][VEC];
-    strip_raw_diffs<T, VEC, SCHEME, Z_ON, T_ON>(d, pl, P, i, j0, o, o_up, o_dn);
+    strip_raw_diffs<T, VEC, SCHEME, Z_ON, T_ON, T, TS>(d, pl, P, i, j0, o, o_up, o_dn);
     Pack<T, VEC> w, n;
     T sum = T(0);
 #pragma unroll
@@ -342,8 +350,8 @@ PYTVB_HD T ld_field1(const YT* src) {
 }
 
 // D^T y at one quad (times inv_div), strip addressing.
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, bool CG = false, typename YT = T>
-PYTVB_HD void strip_quad_DT(T* out, const PrimalPlane<T, YT>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn) {
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, bool CG, typename YT, bool TS>
+PYTVB_HD void strip_quad_DT_impl(T* out, const PrimalPlane<T, YT>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn) {
     typedef Comp<SCHEME, Z_ON, T_ON> C;
     constexpr bool NF = (SCHEME != DOWNWIND);   // reads the forward-type slot at k-1 (centred: C[k-1])
     constexpr bool NB = (SCHEME != UPWIND);     // reads the backward-type slot at k+1 (centred: C[k+1])
@@ -417,7 +425,7 @@ PYTVB_HD void strip_quad_DT(T* out, const PrimalPlane<T, YT>& pl, const Params<T
         if (up_form && NF) ld_field<T, VEC, CG>(f_c, pl.y + (long long)C::T_F * P.sC + o); else zero_into<T, VEC>(f_c);
         if (!CTR && NB) ld_field<T, VEC, CG>(b_c, pl.y + (long long)C::T_B * P.sC + o); else zero_into<T, VEC>(b_c);
         if (NB && !(CTR && fb)) ld_field<T, VEC, CG>(b_p, pl.tb_p + o); else zero_into<T, VEC>(b_p);
-        if (pl.ts_c) {   // exact adjoint of the per-voxel time scale: every entry is scaled where it lives
+        if constexpr (TS) {   // exact adjoint of the per-voxel time scale: every entry is scaled where it lives
             scale_by<T, VEC>(f_m, pl.ts_m, o); scale_by<T, VEC>(f_c, pl.ts_c, o);
             scale_by<T, VEC>(b_c, pl.ts_c, o); scale_by<T, VEC>(b_p, pl.ts_p, o);
         }
@@ -433,14 +441,19 @@ PYTVB_HD void strip_quad_DT(T* out, const PrimalPlane<T, YT>& pl, const Params<T
     for (int e = 0; e < VEC; ++e) out[e] = acc[e] * P.inv_div;
 }
 
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, bool CG = false, typename YT = T, bool TS = false>
+PYTVB_HD void strip_quad_DT(T* out, const PrimalPlane<T, YT>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn) {
+    strip_quad_DT_impl<T, VEC, SCHEME, Z_ON, T_ON, CG, YT, TS && T_ON>(out, pl, P, i, j0, o, o_up, o_dn);
+}
+
 // Primal update at one quad.  VARIANT 0: ROF prox + over-relaxation (aux = xbar); 1: README form (aux = y_f).
 // c1 = 1/(1+tau) (rof) or 1/(1+sigma_A) (readme); c2 = theta or sigma_A.  Returns sum (x_new - x0)^2.
 // `tau` multiplies D^T y: for a normalised half-precision dual the caller passes tau * lam.
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int VARIANT, bool CG = false, typename YT = T>
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int VARIANT, bool CG = false, typename YT = T, bool TS = false>
 PYTVB_HD T strip_quad_cp_primal(T* x, T* aux, const T* x0, const PrimalPlane<T, YT>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn,
                                 T tau, T c1, T c2, T tau_x0 = T(-1)) {
     T dty[VEC];
-    strip_quad_DT<T, VEC, SCHEME, Z_ON, T_ON, CG, YT>(dty, pl, P, i, j0, o, o_up, o_dn);
+    strip_quad_DT<T, VEC, SCHEME, Z_ON, T_ON, CG, YT, TS>(dty, pl, P, i, j0, o, o_up, o_dn);
     if (tau_x0 < T(0)) tau_x0 = tau;
     const long long off = pl.img + o;
     const Pack<T, VEC> xo = ld_pack<T, VEC>(x + off), x0q = ld_pack<T, VEC>(x0 + off);
@@ -526,8 +539,8 @@ PYTVB_HD T strip_g_axis(bool fallback, T a, T b, T xm2, T xm, T xc, T xp, T xp2,
     return a * ((xc - xm2) * wm) - b * ((xp2 - xc) * wp);
 }
 
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON>
-PYTVB_HD void strip_quad_G(T* g_plane, const GradPlane<T>& pl, const Params<T>& P, int i, int j0, int o) {
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, bool TS>
+PYTVB_HD void strip_quad_G_impl(T* g_plane, const GradPlane<T>& pl, const Params<T>& P, int i, int j0, int o) {
     constexpr bool CEN = (SCHEME == CENTRAL);
     const int Nj = P.Nj;
     const int o_up = i > 0 ? o - Nj : o, o_dn = i < P.Ni - 1 ? o + Nj : o;
@@ -584,7 +597,7 @@ PYTVB_HD void strip_quad_G(T* g_plane, const GradPlane<T>& pl, const Params<T>& 
         T wc[VEC];
 #pragma unroll
         for (int e = 0; e < VEC; ++e) wc[e] = wr[e + 1];
-        if (pl.ts_c) {   // q = D w with D scaled where it lives: along t the inverse norms travel with their voxel's scale
+        if constexpr (TS) {   // q = D w with D scaled where it lives: along t the inverse norms travel with their voxel's scale
             scale_by<T, VEC>(wm, pl.ts_m, o); scale_by<T, VEC>(wc, pl.ts_c, o); scale_by<T, VEC>(wp, pl.ts_p, o);
         }
 #pragma unroll
@@ -597,6 +610,11 @@ PYTVB_HD void strip_quad_G(T* g_plane, const GradPlane<T>& pl, const Params<T>& 
 #pragma unroll
     for (int e = 0; e < VEC; ++e) pk.v[e] = g[e] * (P.inv_div * P.inv_div);
     st_pack<T, VEC>(g_plane + o, pk);
+}
+
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, bool TS = false>
+PYTVB_HD void strip_quad_G(T* g_plane, const GradPlane<T>& pl, const Params<T>& P, int i, int j0, int o) {
+    strip_quad_G_impl<T, VEC, SCHEME, Z_ON, T_ON, TS && T_ON>(g_plane, pl, P, i, j0, o);
 }
 
 }  // namespace pytvb

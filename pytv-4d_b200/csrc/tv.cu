@@ -29,12 +29,14 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchTv {
                 constexpr int R = PYTVB_STRIP_R;
                 const Tiling t1 = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.nz, VEC, a.z_lo);
                 if (int rc = check_grid(t1)) return rc;
-                tv_norm_strip_kernel<T, VEC, SCHEME, Z, TT, R><<<(unsigned)t1.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.Wz0, a.norms, a.partial, a.P, t1);
+                if (TT && a.P.tscale) tv_norm_strip_kernel<T, VEC, SCHEME, Z, TT, R, TT><<<(unsigned)t1.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.Wz0, a.norms, a.partial, a.P, t1);
+                else tv_norm_strip_kernel<T, VEC, SCHEME, Z, TT, R, false><<<(unsigned)t1.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.Wz0, a.norms, a.partial, a.P, t1);
                 count_launches(1);
                 PYTVB_CUDA(cudaGetLastError());
                 *a.nblocks_out = t1.nblocks;
                 const Tiling t2 = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.P.Nz, VEC);
-                tv_grad_strip_kernel<T, VEC, SCHEME, Z, TT, R><<<(unsigned)t2.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.W, a.G, a.P, t2);
+                if (TT && a.P.tscale) tv_grad_strip_kernel<T, VEC, SCHEME, Z, TT, R, TT><<<(unsigned)t2.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.W, a.G, a.P, t2);
+                else tv_grad_strip_kernel<T, VEC, SCHEME, Z, TT, R, false><<<(unsigned)t2.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.W, a.G, a.P, t2);
                 count_launches(1);
                 PYTVB_CUDA(cudaGetLastError());
                 return PYTVB_OK;
@@ -91,7 +93,8 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchTvVal {
         constexpr int R = PYTVB_STRIP_R;
         const Tiling tl = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.P.Nz, VEC);
         if (int rc = check_grid(tl)) return rc;
-        tv_norm_strip_kernel<T, VEC, SCHEME, Z, TT, R><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.X, (T*)nullptr, (T*)nullptr, a.partial, a.P, tl);
+        if (TT && a.P.tscale) tv_norm_strip_kernel<T, VEC, SCHEME, Z, TT, R, TT><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.X, (T*)nullptr, (T*)nullptr, a.partial, a.P, tl);
+        else tv_norm_strip_kernel<T, VEC, SCHEME, Z, TT, R, false><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.X, (T*)nullptr, (T*)nullptr, a.partial, a.P, tl);
         count_launches(1);
         PYTVB_CUDA(cudaGetLastError());
         *a.nb = tl.nblocks;

@@ -118,7 +118,7 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct EDual2 {
                 for (int i = 0; i < a.P.Ni; ++i)
                     for (int j0 = 0; j0 < a.P.Nj; j0 += VEC) {
                         const int o = i * a.P.Nj + j0, o_up = i > 0 ? o - a.P.Nj : o, o_dn = i < a.P.Ni - 1 ? o + a.P.Nj : o;
-                        s += (double)strip_quad_cp_dual<T, VEC, SCHEME, Z, TT>(pl, a.P, i, j0, o, o_up, o_dn, a.c0 * a.P.inv_div, T(1) / a.c1);
+                        s += (double)(a.P.tscale ? strip_quad_cp_dual<T, VEC, SCHEME, Z, TT, T, true>(pl, a.P, i, j0, o, o_up, o_dn, a.c0 * a.P.inv_div, T(1) / a.c1) : strip_quad_cp_dual<T, VEC, SCHEME, Z, TT, T, false>(pl, a.P, i, j0, o, o_up, o_dn, a.c0 * a.P.inv_div, T(1) / a.c1));
                     }
             }
         *a.sum = s * (double)a.P.inv_div;
@@ -136,9 +136,9 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct EPrimal2 {
                     for (int j0 = 0; j0 < a.P.Nj; j0 += VEC) {
                         const int o = i * a.P.Nj + j0, o_up = i > 0 ? o - a.P.Nj : o, o_dn = i < a.P.Ni - 1 ? o + a.P.Nj : o;
                         if (a.variant == 0)
-                            s += (double)strip_quad_cp_primal<T, VEC, SCHEME, Z, TT, 0>(a.out, a.aux, a.x0, pl, a.P, i, j0, o, o_up, o_dn, a.c0, c1, a.c1);
+                            s += (double)(a.P.tscale ? strip_quad_cp_primal<T, VEC, SCHEME, Z, TT, 0, false, T, true>(a.out, a.aux, a.x0, pl, a.P, i, j0, o, o_up, o_dn, a.c0, c1, a.c1) : strip_quad_cp_primal<T, VEC, SCHEME, Z, TT, 0, false, T, false>(a.out, a.aux, a.x0, pl, a.P, i, j0, o, o_up, o_dn, a.c0, c1, a.c1));
                         else
-                            s += (double)strip_quad_cp_primal<T, VEC, SCHEME, Z, TT, 1>(a.out, a.aux, a.x0, pl, a.P, i, j0, o, o_up, o_dn, a.c0, c1, a.c1);
+                            s += (double)(a.P.tscale ? strip_quad_cp_primal<T, VEC, SCHEME, Z, TT, 1, false, T, true>(a.out, a.aux, a.x0, pl, a.P, i, j0, o, o_up, o_dn, a.c0, c1, a.c1) : strip_quad_cp_primal<T, VEC, SCHEME, Z, TT, 1, false, T, false>(a.out, a.aux, a.x0, pl, a.P, i, j0, o, o_up, o_dn, a.c0, c1, a.c1));
                     }
             }
         *a.sum = s;
@@ -160,7 +160,7 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct ED2 {
     static int run(const EArgs<T>& a) {
         for_each_quad_strip(0, a.P.Nz, a.P.M, a.P.Ni, a.P.Nj, VEC, [&](int z, int t, int i, int j0, int o, int o_up, int o_dn) {
             const DualPlane<T> pl = make_dual_plane<T, SCHEME>(a.X, a.out, a.P, z, t);
-            strip_quad_D<T, VEC, SCHEME, Z, TT>(pl.y, pl, a.P, i, j0, o, o_up, o_dn);
+            if (a.P.tscale) strip_quad_D<T, VEC, SCHEME, Z, TT, true>(pl.y, pl, a.P, i, j0, o, o_up, o_dn); else strip_quad_D<T, VEC, SCHEME, Z, TT, false>(pl.y, pl, a.P, i, j0, o, o_up, o_dn);
         });
         return 0;
     }
@@ -170,7 +170,7 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct EDT2 {
         for_each_quad_strip(0, a.P.Nz, a.P.M, a.P.Ni, a.P.Nj, VEC, [&](int z, int t, int i, int j0, int o, int o_up, int o_dn) {
             const PrimalPlane<T> pl = make_primal_plane<T, SCHEME, Z, TT>(a.F, a.P, z, t);
             T v[VEC];
-            strip_quad_DT<T, VEC, SCHEME, Z, TT>(v, pl, a.P, i, j0, o, o_up, o_dn);
+            if (a.P.tscale) strip_quad_DT<T, VEC, SCHEME, Z, TT, false, T, true>(v, pl, a.P, i, j0, o, o_up, o_dn); else strip_quad_DT<T, VEC, SCHEME, Z, TT, false, T, false>(v, pl, a.P, i, j0, o, o_up, o_dn);
             for (int e = 0; e < VEC; ++e) a.out[pl.img + o + e] = v[e];
         });
         return 0;
@@ -184,12 +184,12 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct ETV2 {
             const DualPlane<T> pl = make_dual_plane<T, SCHEME>(a.X, Wz0, a.P, z, t);
             const long long img = (long long)z * a.P.sZ + (long long)t * a.P.sT;
             const bool own = z >= 0 && z < a.P.Nz;
-            const T v = strip_quad_tv_norm<T, VEC, SCHEME, Z, TT>(Wz0 + img, (a.out2 && own) ? a.out2 + img : nullptr, pl, a.P, i, j0, o, o_up, o_dn);
+            const T v = (a.P.tscale ? strip_quad_tv_norm<T, VEC, SCHEME, Z, TT, true>(Wz0 + img, (a.out2 && own) ? a.out2 + img : nullptr, pl, a.P, i, j0, o, o_up, o_dn) : strip_quad_tv_norm<T, VEC, SCHEME, Z, TT, false>(Wz0 + img, (a.out2 && own) ? a.out2 + img : nullptr, pl, a.P, i, j0, o, o_up, o_dn));
             if (own) tv += (double)v;
         });
         for_each_quad_strip(0, a.P.Nz, a.P.M, a.P.Ni, a.P.Nj, VEC, [&](int z, int t, int i, int j0, int o, int, int) {
             const GradPlane<T> pl = make_grad_plane<T, SCHEME>(a.X, a.W, a.P, z, t);
-            strip_quad_G<T, VEC, SCHEME, Z, TT>(a.out + (long long)z * a.P.sZ + (long long)t * a.P.sT, pl, a.P, i, j0, o);
+            if (a.P.tscale) strip_quad_G<T, VEC, SCHEME, Z, TT, true>(a.out + (long long)z * a.P.sZ + (long long)t * a.P.sT, pl, a.P, i, j0, o); else strip_quad_G<T, VEC, SCHEME, Z, TT, false>(a.out + (long long)z * a.P.sZ + (long long)t * a.P.sT, pl, a.P, i, j0, o);
         });
         *a.sum = tv;
         return 0;
@@ -237,7 +237,7 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct EFused {
                         const int i = strip * R + r;
                         if (i < a.P.Ni) {
                             const int o = i * a.P.Nj + j0;
-                            l21 += (double)strip_quad_cp_dual<T, VEC, SCHEME, Z, TT>(pl, a.P, i, j0, o, i > 0 ? o - a.P.Nj : o, i < a.P.Ni - 1 ? o + a.P.Nj : o, sig, a.lam);
+                            l21 += (double)(a.P.tscale ? strip_quad_cp_dual<T, VEC, SCHEME, Z, TT, T, true>(pl, a.P, i, j0, o, i > 0 ? o - a.P.Nj : o, i < a.P.Ni - 1 ? o + a.P.Nj : o, sig, a.lam) : strip_quad_cp_dual<T, VEC, SCHEME, Z, TT, T, false>(pl, a.P, i, j0, o, i > 0 ? o - a.P.Nj : o, i < a.P.Ni - 1 ? o + a.P.Nj : o, sig, a.lam));
                         }
                     }
                 } else {
@@ -248,8 +248,8 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct EFused {
                         if (i >= 0 && i < a.P.Ni) {
                             const int o = i * a.P.Nj + j0;
                             const int ou = i > 0 ? o - a.P.Nj : o, od = i < a.P.Ni - 1 ? o + a.P.Nj : o;
-                            if (a.variant == 0) fid += (double)strip_quad_cp_primal<T, VEC, SCHEME, Z, TT, 0>(a.x, a.aux, a.x0, pl, a.P, i, j0, o, ou, od, a.tau, c1, a.c2);
-                            else fid += (double)strip_quad_cp_primal<T, VEC, SCHEME, Z, TT, 1>(a.x, a.aux, a.x0, pl, a.P, i, j0, o, ou, od, a.tau, c1, a.c2);
+                            if (a.variant == 0) fid += (double)(a.P.tscale ? strip_quad_cp_primal<T, VEC, SCHEME, Z, TT, 0, false, T, true>(a.x, a.aux, a.x0, pl, a.P, i, j0, o, ou, od, a.tau, c1, a.c2) : strip_quad_cp_primal<T, VEC, SCHEME, Z, TT, 0, false, T, false>(a.x, a.aux, a.x0, pl, a.P, i, j0, o, ou, od, a.tau, c1, a.c2));
+                            else fid += (double)(a.P.tscale ? strip_quad_cp_primal<T, VEC, SCHEME, Z, TT, 1, false, T, true>(a.x, a.aux, a.x0, pl, a.P, i, j0, o, ou, od, a.tau, c1, a.c2) : strip_quad_cp_primal<T, VEC, SCHEME, Z, TT, 1, false, T, false>(a.x, a.aux, a.x0, pl, a.P, i, j0, o, ou, od, a.tau, c1, a.c2));
                         }
                     }
                 }
