@@ -144,3 +144,31 @@ def test_cp_iteration_on_C4_slab_equals_two_half_slabs():
     assert 0.5 * fid + 0.1 * l21 == pytest.approx(e_whole, rel=1e-12)
     del s, x, y, xbar
     _free()
+
+
+def test_cp_passes_stay_at_the_hbm_roofline():
+    """Performance guard (loose): on the C4 slab both Chambolle-Pock passes must sustain at least 85 % of the measured HBM
+    copy bandwidth (they run at 98-99 %; a refactoring once cost pass B 12 % unnoticed)."""
+    import json
+    import os
+    shape, kw = C4
+    try:
+        peak = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        peak = 6650.0
+    torch.manual_seed(4)
+    x0 = torch.rand(shape, device="cuda")
+    s = pytv.CPSolver(x0, lam=0.1, scheme="hybrid", variant="rof", fused=False, **kw)
+    s.step(3)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    tA = tB = 0.0
+    for _ in range(5):
+        ev[0].record(); s._pass_A(); ev[1].record(); s._pass_B(); ev[2].record()
+        torch.cuda.synchronize()
+        tA += ev[0].elapsed_time(ev[1]); tB += ev[1].elapsed_time(ev[2])
+    V = x0.numel()
+    fracA = 4.0 * (2 * 8 + 1) * V / (tA / 5 * 1e-3) / 1e9 / peak
+    fracB = 4.0 * (8 + 4) * V / (tB / 5 * 1e-3) / 1e9 / peak
+    del s
+    _free()
+    assert fracA > 0.85 and fracB > 0.85, (fracA, fracB)
