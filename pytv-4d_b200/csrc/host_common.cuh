@@ -56,6 +56,7 @@ inline int check_problem(const pytvb_problem* pb) {
     PYTVB_REQUIRE(pb->Nz >= 1 && pb->M >= 1 && pb->Ni >= 1 && pb->Nj >= 1, "empty volume %lld x %lld x %lld x %lld",
                   (long long)pb->Nz, (long long)pb->M, (long long)pb->Ni, (long long)pb->Nj);
     PYTVB_REQUIRE(pb->Nz < (1LL << 30) && pb->M < (1LL << 30) && pb->Ni < (1LL << 30) && pb->Nj < (1LL << 30), "extent too large");
+    PYTVB_REQUIRE(pb->Ni * pb->Nj < (1LL << 31) - 8, "one image plane must have fewer than 2^31 pixels (offsets inside a plane are 32-bit)");
     PYTVB_REQUIRE(pb->z_offset >= 0 && pb->z_offset + pb->Nz <= pb->Nz_global, "slab [%lld, %lld) outside 0..%lld",
                   (long long)pb->z_offset, (long long)(pb->z_offset + pb->Nz), (long long)pb->Nz_global);
     PYTVB_REQUIRE(!(pb->factor_reg_static < 0), "factor_reg_static must be >= 0");

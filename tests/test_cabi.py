@@ -62,6 +62,8 @@ def test_argument_errors_are_reported():
     p = buf.ctypes.data_as(ctypes.c_void_p)
     assert lib.pytvb_D(ctypes.byref(slab), p, p, None, None, None) == -1
     assert b"halo_lo is required" in lib.pytvb_last_error()
+    huge = _lib.make_problem("hybrid", _lib.F32, (1, 1, 1 << 16, 1 << 16))
+    assert lib.pytvb_num_components(ctypes.byref(huge)) == -1 and b"2^31" in lib.pytvb_last_error()
     outside = _lib.make_problem("hybrid", _lib.F32, (4, 1, 8, 8), z_offset=2, Nz_global=4)
     assert lib.pytvb_num_components(ctypes.byref(outside)) == -1
     with pytest.raises(_lib.PytvError):
