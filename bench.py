@@ -387,8 +387,6 @@ def run_ours(args):
                                "traffic": traffic.get("cp_primal_kernel") if traffic else None},
                     "iteration": {"algorithmic_bytes": dual_bytes + primal_bytes, "achieved": (dual_bytes + primal_bytes) * K / (t_ms * 1e-3) / 1e9,
                                   "frac": (dual_bytes + primal_bytes) * K / (t_ms * 1e-3) / 1e9 / peak}}
-        if solver.fused:
-            pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W, "ms_per_step": t_ms / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config_dict(n_gpus, {"slab_per_gpu": list(shape), "energy_last": energy}),

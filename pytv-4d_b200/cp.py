@@ -17,7 +17,6 @@ z-neighbours, before pass B the boundary planes of the z-components of y; the en
 of two doubles.  M and N are never split.  With the z axis off the slabs are independent.
 """
 import ctypes
-import math
 import os
 
 import numpy as np
@@ -655,7 +654,6 @@ def gd_denoise(x0, lam, n_iter, step, scheme="hybrid", return_pytorch_tensor=Fal
         tv, G = tv_<scheme>(x);  x <- x - step ((x - x0) + lam G);  loss = 0.5 |x - x0|^2 + lam tv
     `weights`: reg_z_over_reg, reg_time, mask_static, factor_reg_static.  Returns x (and the loss history, one entry per
     iteration, read back once at the end)."""
-    from . import tv_GPU   # noqa: F401  (same kernels as the drop-in call)
     x0d, was_tensor = _dev.to_device(x0)
     shape = _dev.image_shape(x0d)
     lib = _lib.lib()
