@@ -98,11 +98,21 @@ def _cpu_worker(args):
     return time.perf_counter() - t0, kind, e
 
 
+def _cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def cpu_baseline_single(sample_shape=(8, 4, 512, 512), steps=7, warmup=1):
     """Single-process run of the CPU implementation, as shipped (numpy element-wise kernels: one busy core)."""
     dt, kind, _ = _cpu_worker((1000, sample_shape, steps, warmup))
     vox = int(np.prod(sample_shape))
-    return {"value": vox * steps / dt, "unit": UNIT, "cores": 1, "kind": kind,
+    return {"value": vox * steps / dt, "unit": UNIT, "cores": 1, "kind": kind, "host_cpu": _cpu_model(), "host_cpu_count": os.cpu_count(),
             "sample": "%d CP-ROF iterations on a %s float32 sample slab of the same workload (hybrid, reg_time=2^-5, Nd=8), %.1f s"
                       % (steps, "x".join(map(str, sample_shape)), dt)}
 
@@ -137,7 +147,7 @@ def run_reference_arm(args):
             "ms_per_step": 1e3 * t_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": config_dict(args.gpus, {"note": "CPU arm: bounded sample of the workload, %d processes x slab %s" % (procs, list(sample))}),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "host_cpu": _cpu_model(), "host_cpu_count": os.cpu_count(),
                              "sample": "%d processes (of %d host cores), each %d CP-ROF iterations on its own %s float32 slab; wall %.1f s"
                                        % (procs, cores, steps, "x".join(map(str, sample)), wall)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
