@@ -262,8 +262,9 @@ def run_ours(args):
     # ---- synthetic data, seeded per rank (uniform [0,1) + 0.05 randn, seed 1000+rank)
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     x0 = torch.rand(shape, generator=g, device=dev) + 0.05 * torch.randn(shape, generator=g, device=dev)
+    comm = args.comm if world > 1 else "nccl"
     solver = pytv.CPSolver(x0, lam=LAM, scheme="hybrid", variant="rof", reg_time=REG_TIME, distributed=(world > 1),
-                           z_offset=rank * shape[0], Nz_global=world * shape[0])
+                           z_offset=rank * shape[0], Nz_global=world * shape[0], comm=comm)
     del x0
     assert solver.Nd == 8 or args.slab
     lib = _lib.lib()
@@ -310,8 +311,13 @@ def run_ours(args):
     energy = solver.energy()
     dual_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
     primal_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / K
+    per_rank = None
     if world > 1:
-        t = torch.tensor([t_ms, dual_ms, primal_ms], dtype=torch.float64, device=dev)
+        mine = torch.tensor([t_ms, dual_ms, primal_ms], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"total_ms": [float(a[0]) for a in allr], "pass_A_ms": [float(a[1]) for a in allr], "pass_B_ms": [float(a[2]) for a in allr]}
+        t = mine.clone()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_ms, dual_ms, primal_ms = t.tolist()
     value = V_local * world * K / (t_ms * 1e-3)
@@ -399,7 +405,8 @@ def run_ours(args):
                                   "frac": (dual_bytes + primal_bytes) * K / (t_ms * 1e-3) / 1e9 / peak}}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W, "ms_per_step": t_ms / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": config_dict(n_gpus, {"slab_per_gpu": list(shape), "energy_last": energy}),
+                "config": config_dict(n_gpus, {"slab_per_gpu": list(shape), "energy_last": energy,
+                                               "halo_comm": "none (one GPU)" if world == 1 else comm}),
                 "roofline": roofline,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": img_bytes * world, "d2h_bytes_per_step": (img_bytes + 16) * world,
                         "ms_per_step": 1e3 * e2e_s / K, "ms_per_step_unpipelined": e2e_sync_ms,
@@ -408,6 +415,8 @@ def run_ours(args):
                 "gpu_launches": int(launches), "clocks": clocks}
         if extras:
             line["extras"] = extras
+        if per_rank:
+            line["per_rank"] = per_rank      # event times of every rank (the headline uses the max)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single()
         print(json.dumps(line), flush=True)
@@ -422,6 +431,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--comm", choices=["nccl", "p2p"], default=os.environ.get("PYTVB_BENCH_COMM", "nccl"),
+                    help="N > 1: halo planes by NCCL send/recv between the passes, or pushed by the kernels into peer memory")
     ap.add_argument("--slab", type=int, nargs=4, default=None, help="override the per-GPU slab (Nz M Ni Nj); debugging only")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline leg (profiling runs)")
     ap.add_argument("--no-extras", action="store_true", help="skip the informational reduced-precision measurement")

@@ -113,6 +113,20 @@ int pytvb_cp_primal_readme(const pytvb_problem* pb, const void* y_tv, void* x, v
                            double sigma_A, double* d_fid_or_null, const void* halo_lo, const void* halo_hi, void* ws,
                            void* stream);
 
+/* Multi-GPU without an exchange step ("peer-memory halo push"): the same passes, but the kernel stores the boundary
+ * planes a z-neighbour will read as its halos a second time, directly into that neighbour's halo buffer.
+ * mirror_prev / mirror_next: peer-mapped DEVICE pointers (CUDA IPC / symmetric memory; NVLink) to one (M, Ni, Nj) plane in the
+ * previous / next rank, or NULL.  Pass A pushes the backward-type z component of local plane 0 (the previous rank's field
+ * halo_hi) and the forward-type z component of the last plane (the next rank's field halo_lo); pass B pushes plane 0 / the last
+ * plane of the image the next dual pass differentiates (xbar for variant 0, x for variant 1) into the neighbours' image halo_hi /
+ * halo_lo.  The caller separates the passes with a cross-rank barrier on the stream (no data moves in it).  Not combinable with
+ * time_scale. */
+int pytvb_cp_dual_p2p(const pytvb_problem* pb, const void* xbar, void* y, double lam, double sigma, double* d_l21_or_null,
+                      const void* halo_lo, const void* halo_hi, void* mirror_prev, void* mirror_next, void* ws, void* stream);
+int pytvb_cp_primal_p2p(const pytvb_problem* pb, int variant, const void* y, void* x, void* aux, const void* x0, double tau, double c2,
+                        double* d_fid_or_null, const void* halo_lo, const void* halo_hi, void* mirror_prev, void* mirror_next, void* ws,
+                        void* stream);
+
 /* Half-precision STORAGE of the dual field: float32 images and arithmetic, y kept as IEEE half in the
  * same (Nz, Nd, M, Ni, Nj) layout, normalised to the unit ball (the array holds y / lam).  Halves the dominant
  * traffic: 4(3Nd+5) -> 6Nd+20 bytes per voxel (68 instead of 116 for Nd = 8).  NOT within the 1e-5 parity

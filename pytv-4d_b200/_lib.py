@@ -61,6 +61,8 @@ _PROTOTYPES = {
     "pytvb_cp_dual": (ctypes.c_int, [_PB, _VP, _VP, ctypes.c_double, ctypes.c_double, _VP, _VP, _VP, _VP, _VP]),
     "pytvb_cp_primal_rof": (ctypes.c_int, [_PB, _VP, _VP, _VP, _VP, ctypes.c_double, ctypes.c_double, _VP, _VP, _VP, _VP, _VP]),
     "pytvb_cp_primal_readme": (ctypes.c_int, [_PB, _VP, _VP, _VP, _VP, ctypes.c_double, ctypes.c_double, _VP, _VP, _VP, _VP, _VP]),
+    "pytvb_cp_dual_p2p": (ctypes.c_int, [_PB, _VP, _VP, ctypes.c_double, ctypes.c_double, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "pytvb_cp_primal_p2p": (ctypes.c_int, [_PB, ctypes.c_int, _VP, _VP, _VP, _VP, ctypes.c_double, ctypes.c_double, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "pytvb_cp_dual_f16y": (ctypes.c_int, [_PB, _VP, _VP, ctypes.c_double, ctypes.c_double, _VP, _VP, _VP, _VP, _VP]),
     "pytvb_cp_primal_rof_f16y": (ctypes.c_int, [_PB, _VP, _VP, _VP, _VP, ctypes.c_double, ctypes.c_double, ctypes.c_double, _VP, _VP, _VP, _VP, _VP]),
     "pytvb_fused_workspace_bytes": (ctypes.c_size_t, [_PB]),

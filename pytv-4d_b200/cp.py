@@ -71,6 +71,15 @@ class CudaOps:
         _lib.check(fn(ctypes.byref(pb), _dev.ptr(y), _dev.ptr(x), _dev.ptr(aux), _dev.ptr(x0), tau, c2, _dev.ptr(d_fid), _dev.ptr(lo), _dev.ptr(hi),
                       _dev.ptr(ws), _dev.stream_ptr()))
 
+    def cp_dual_p2p(self, pb, xbar, y, lam, sigma, d_l21, lo, hi, mirror_prev, mirror_next, ws):
+        _lib.check(self.lib.pytvb_cp_dual_p2p(ctypes.byref(pb), _dev.ptr(xbar), _dev.ptr(y), lam, sigma, _dev.ptr(d_l21), _dev.ptr(lo), _dev.ptr(hi),
+                                              mirror_prev, mirror_next, _dev.ptr(ws), _dev.stream_ptr()))
+
+    def cp_primal_p2p(self, variant, pb, y, x, aux, x0, tau, c2, d_fid, lo, hi, mirror_prev, mirror_next, ws):
+        _lib.check(self.lib.pytvb_cp_primal_p2p(ctypes.byref(pb), 0 if variant == "rof" else 1, _dev.ptr(y), _dev.ptr(x), _dev.ptr(aux), _dev.ptr(x0),
+                                                tau, c2, _dev.ptr(d_fid), _dev.ptr(lo), _dev.ptr(hi), mirror_prev, mirror_next, _dev.ptr(ws),
+                                                _dev.stream_ptr()))
+
     def workspace(self, pb, device):
         return _dev.reduce_workspace(pb, device)
 
@@ -146,6 +155,33 @@ class HaloExchange:
         return self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self._reduce_group, async_op=True)
 
 
+class PeerHalos:
+    """The four halo planes of a rank, [img_lo, img_hi, fld_lo, fld_hi], in symmetric memory (torch.distributed.
+    _symmetric_memory: cuMem allocations mapped into every rank of the node over NVLink).  The passes of the
+    neighbouring ranks store into these planes directly (`peer`), the local passes read them (`local`); `barrier` is
+    the cross-rank fence between passes (a one-CTA kernel on the current stream, no data)."""
+    IMG_LO, IMG_HI, FLD_LO, FLD_HI = 0, 1, 2, 3
+
+    def __init__(self, halo, plane, dtype, device):
+        import torch.distributed._symmetric_memory as symm
+        group = halo.group if halo.group is not None else halo.dist.group.WORLD
+        self.buf = symm.empty((4,) + tuple(plane), dtype=dtype, device=device)
+        self.hdl = symm.rendezvous(self.buf, group)
+        self.buf.zero_()
+        self.plane_bytes = self.buf[0].numel() * self.buf.element_size()
+        self.timeout_ms = int(os.environ.get("PYTVB_P2P_TIMEOUT_MS", "60000"))   # a lost rank traps instead of hanging the GPU
+
+    def local(self, slot):
+        return self.buf[slot]
+
+    def peer(self, rank, slot):
+        """Address of plane `slot` of rank `rank` (rank within the solver's group) as mapped into this process."""
+        return None if rank is None else int(self.hdl.buffer_ptrs[rank]) + slot * self.plane_bytes
+
+    def barrier(self):
+        self.hdl.barrier(channel=0, timeout_ms=self.timeout_ms)
+
+
 class CPSolver:
     """Device-resident Chambolle-Pock state for one volume, or for this rank's z-slab of a sharded volume.
 
@@ -156,7 +192,7 @@ class CPSolver:
 
     def __init__(self, x0, lam, scheme="hybrid", variant="rof", sigma=0.5, tau=None, theta=1.0, sigma_A=1.0, reg_z_over_reg=1.0,
                  reg_time=0.0, mask_static=False, factor_reg_static=0, distributed=False, group=None, z_offset=None, Nz_global=None,
-                 ops=None, track_energy=True, fused=None, dual_dtype=None, time_weight=None):
+                 ops=None, track_energy=True, fused=None, dual_dtype=None, time_weight=None, comm=None):
         if scheme not in _dev.SCHEMES:
             raise ValueError("unknown scheme %r" % (scheme,))
         if variant not in ("rof", "readme"):
@@ -240,18 +276,37 @@ class CPSolver:
         self.fused = bool(fused) and self.halo is None and hasattr(self.ops, "cp_iter_fused") and self.dual_dtype == dt
         self._fused_ws = self.ops.fused_workspace(self.pb, dev) if self.fused else None
         self.iterations = 0
-        # halo planes
+        # halo planes.  comm="p2p" (or PYTVB_P2P=1): no exchange step at all - the planes live in symmetric memory and the
+        # passes of the neighbouring ranks store into them (PeerHalos); comm="nccl": send/recv between the passes.
         self._img_lo = self._img_hi = self._fld_lo = self._fld_hi = None
+        self._peer = None
+        if comm is None:
+            comm = "p2p" if os.environ.get("PYTVB_P2P", "0") == "1" else "nccl"
+        if comm not in ("nccl", "p2p"):
+            raise ValueError("comm must be 'nccl' or 'p2p'")
         if self.halo is not None and self.z_on:
             plane = (shape[1], shape[2], shape[3])
             interior_lo, interior_hi = self.halo.prev is not None, self.halo.next is not None
             need_img_lo, need_img_hi = scheme != "upwind", scheme != "downwind"
             need_fld_lo, need_fld_hi = scheme != "downwind", scheme != "upwind"
-            mk = lambda d=dt: torch.empty(plane, dtype=d, device=dev)
-            self._img_lo = mk() if (interior_lo and need_img_lo) else None
-            self._img_hi = mk() if (interior_hi and need_img_hi) else None
-            self._fld_lo = mk(self.dual_dtype) if (interior_lo and need_fld_lo) else None
-            self._fld_hi = mk(self.dual_dtype) if (interior_hi and need_fld_hi) else None
+            if comm == "p2p":
+                if ops is not None or self._ts is not None or self.dual_dtype != dt or self.overlap:
+                    raise ValueError("comm='p2p' needs the CUDA executor, the blocking schedule, no time_weight and full-precision duals")
+                self._peer = PeerHalos(self.halo, plane, dt, dev)
+                mk = lambda d=dt, slot=0: self._peer.local(slot)
+            else:
+                mk = lambda d=dt, slot=0: torch.empty(plane, dtype=d, device=dev)
+            self._img_lo = mk(slot=0) if (interior_lo and need_img_lo) else None
+            self._img_hi = mk(slot=1) if (interior_hi and need_img_hi) else None
+            self._fld_lo = mk(self.dual_dtype, 2) if (interior_lo and need_fld_lo) else None
+            self._fld_hi = mk(self.dual_dtype, 3) if (interior_hi and need_fld_hi) else None
+            if self._peer is not None:
+                P, h = self._peer, self.halo
+                # pass A pushes: my backward-type z slot of plane 0 is the previous rank's fld_hi, my forward-type slot of
+                # the last plane the next rank's fld_lo.  Pass B pushes: my first plane is the previous rank's img_hi, my
+                # last plane the next rank's img_lo.
+                self._mir_A = (P.peer(h.prev, P.FLD_HI) if need_fld_hi else None, P.peer(h.next, P.FLD_LO) if need_fld_lo else None)
+                self._mir_B = (P.peer(h.prev, P.IMG_HI) if need_img_hi else None, P.peer(h.next, P.IMG_LO) if need_img_lo else None)
         self._zf = 4 if scheme == "hybrid" else 2   # forward-type z slot of y
         self._zb = 5 if scheme == "hybrid" else 2   # backward-type z slot
 
@@ -262,11 +317,12 @@ class CPSolver:
     # -- halo traffic.  Image halos: my first plane is the previous rank's halo_hi (needed unless downwind), my last
     # plane the next rank's halo_lo (unless upwind).  Field halos: the neighbour's adjoint reads my backward-type z
     # slot at its z = Nz (unless upwind) and my forward-type z slot at its z = -1 (unless downwind).
-    def _start_image_exchange(self):
+    def _image_planes(self):
         src = self._dual_input()
-        to_prev = src[0] if self.scheme != "downwind" else None
-        to_next = src[-1] if self.scheme != "upwind" else None
-        return self.halo.start_exchange(to_prev, to_next, self._img_lo, self._img_hi)
+        return (src[0] if self.scheme != "downwind" else None, src[-1] if self.scheme != "upwind" else None)
+
+    def _start_image_exchange(self):
+        return self.halo.start_exchange(*self._image_planes(), self._img_lo, self._img_hi)
 
     def _start_field_exchange(self):
         to_prev = self.y[0, self._zb] if self.scheme != "upwind" else None
@@ -322,12 +378,26 @@ class CPSolver:
         if self.halo is None or not self.z_on:
             self._dual_range(0, Nz, 0)
             return
-        if self._pending is None:                      # first iteration (or after a reset): blocking exchange
-            self._pending = self._start_image_exchange()
-        self.halo.finish(self._pending)
-        self._pending = None
+        if self._peer is None:
+            if self._pending is None:                  # first iteration (or after a reset): blocking exchange
+                self._pending = self._start_image_exchange()
+            self.halo.finish(self._pending)
+            self._pending = None
         if self.track_energy:
             self.scal[0:3].zero_()
+        if self._peer is not None:
+            # no exchange: the image halos were stored here by the neighbours' pass B (by one NCCL exchange at start-up),
+            # this pass stores the field halos of the neighbours' pass B; the barrier orders the two across ranks
+            if self._pending is None:
+                self.halo.exchange(*self._image_planes(), self._img_lo, self._img_hi)
+                self._peer.barrier()
+            self._pending = ()
+            d = self.scal[0:1] if self.track_energy else None
+            self.ops.cp_dual_p2p(self.pb, self._dual_input(), self.y, self.lam, self.sigma, d, self._img_lo, self._img_hi, self._mir_A[0],
+                                 self._mir_A[1], self.ws)
+            self._peer.barrier()
+            self._field_req = ()
+            return
         if not self._split():
             self._dual_range(0, Nz, 0)
             self._field_req = self._start_field_exchange()
@@ -348,6 +418,14 @@ class CPSolver:
         self._field_req = None
         if self.track_energy:
             self.scal[3:6].zero_()
+        if self._peer is not None:
+            d = self.scal[3:4] if self.track_energy else None
+            c2 = self.theta if self.variant == "rof" else self.sigma_A
+            self.ops.cp_primal_p2p(self.variant, self.pb, self.y, self.x, self.aux, self.x0, self.tau, c2, d, self._fld_lo, self._fld_hi,
+                                   self._mir_B[0], self._mir_B[1], self.ws)
+            self._peer.barrier()
+            self._pending = ()
+            return
         if not self._split():
             self._primal_range(0, Nz, 0)
             self._pending = self._start_image_exchange()

@@ -34,13 +34,16 @@ inline Tiling make_strip_tiling(int Nj, int Ni, int M, int nz, int vec, int z_lo
     return t;
 }
 
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, typename YT = T, bool TS = false>
+
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, typename YT = T, bool TS = false, bool MIR = false>
 __global__ void __launch_bounds__(CTA_THREADS, PYTVB_DUAL_MINB) cp_dual_strip_kernel(ImgView<T> Xb, YT* __restrict__ y, double* __restrict__ partial, Params<T> P, T sig,
-                                                                    T lam, Tiling tl) {
+                                                                    T lam, Tiling tl, MirrorBufs<YT> mb = MirrorBufs<YT>{nullptr, nullptr}) {
     const QuadIdx q = decode_quad(tl, (P.Ni + R - 1) / R, VEC);   // q.i = strip index
     T l21 = T(0);
     if (q.active) {
         const DualPlane<T, YT> pl = make_dual_plane<T, SCHEME, YT>(Xb, y, P, q.z, q.t);
+        MirrorPlanes<YT> mir{nullptr, nullptr};
+        if constexpr (MIR) mir = mirror_planes<YT>(mb, P, q.z, q.t);
         const int i0 = q.i * R;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -49,7 +52,7 @@ __global__ void __launch_bounds__(CTA_THREADS, PYTVB_DUAL_MINB) cp_dual_strip_ke
                 const int o = i * P.Nj + q.j0;
                 const int o_up = i > 0 ? o - P.Nj : o;
                 const int o_dn = i < P.Ni - 1 ? o + P.Nj : o;
-                l21 += strip_quad_cp_dual<T, VEC, SCHEME, Z_ON, T_ON, YT, TS>(pl, P, i, q.j0, o, o_up, o_dn, sig, lam);
+                l21 += strip_quad_cp_dual<T, VEC, SCHEME, Z_ON, T_ON, YT, TS, MIR>(pl, P, i, q.j0, o, o_up, o_dn, sig, lam, mir);
             }
         }
     }
@@ -59,13 +62,16 @@ __global__ void __launch_bounds__(CTA_THREADS, PYTVB_DUAL_MINB) cp_dual_strip_ke
     }
 }
 
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int VARIANT, int R, typename YT = T, bool TS = false>
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int VARIANT, int R, typename YT = T, bool TS = false, bool MIR = false>
 __global__ void __launch_bounds__(CTA_THREADS, PYTVB_PRIMAL_MINB) cp_primal_strip_kernel(FieldView<YT> Y, T* __restrict__ x, T* __restrict__ aux, const T* __restrict__ x0,
-                                                                      double* __restrict__ partial, Params<T> P, T tau, T c1, T c2, Tiling tl, T tau_x0 = T(-1)) {
+                                                                      double* __restrict__ partial, Params<T> P, T tau, T c1, T c2, Tiling tl, T tau_x0 = T(-1),
+                                                                      MirrorBufs<T> mb = MirrorBufs<T>{nullptr, nullptr}) {
     const QuadIdx q = decode_quad(tl, (P.Ni + R - 1) / R, VEC);
     T fid = T(0);
     if (q.active) {
         const PrimalPlane<T, YT> pl = make_primal_plane<T, SCHEME, Z_ON, T_ON, YT>(Y, P, q.z, q.t);
+        MirrorPlanes<T> mir{nullptr, nullptr};
+        if constexpr (MIR) mir = mirror_planes<T>(mb, P, q.z, q.t);
         const int i0 = q.i * R;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -74,7 +80,7 @@ __global__ void __launch_bounds__(CTA_THREADS, PYTVB_PRIMAL_MINB) cp_primal_stri
                 const int o = i * P.Nj + q.j0;
                 const int o_up = i > 0 ? o - P.Nj : o;
                 const int o_dn = i < P.Ni - 1 ? o + P.Nj : o;
-                fid += strip_quad_cp_primal<T, VEC, SCHEME, Z_ON, T_ON, VARIANT, false, YT, TS>(x, aux, x0, pl, P, i, q.j0, o, o_up, o_dn, tau, c1, c2, tau_x0);
+                fid += strip_quad_cp_primal<T, VEC, SCHEME, Z_ON, T_ON, VARIANT, false, YT, TS, MIR>(x, aux, x0, pl, P, i, q.j0, o, o_up, o_dn, tau, c1, c2, tau_x0, mir);
             }
         }
     }

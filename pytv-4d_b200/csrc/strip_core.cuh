@@ -180,8 +180,32 @@ PYTVB_HD void strip_raw_diffs(T (*d)[VEC], const DualPlane<T, YT>& pl, const Par
 
 // One quad of the dual pass.  sig = sigma * inv_div (so that y + sigma*D = y + sig*raw_difference).
 // Returns sum_e sqrt(sum_k raw_k^2) (the caller multiplies the total by inv_div to get L21(D xbar)).
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, typename YT = T, bool TS = false>
-PYTVB_HD T strip_quad_cp_dual(const DualPlane<T, YT>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn, T sig, T lam) {
+// Peer-memory halo push (multi-GPU, opt-in): the boundary planes a neighbouring rank will read as its halos are
+// stored a second time, straight into that rank's halo buffer (a peer-mapped pointer over NVLink), by the kernel that
+// produces them - no separate exchange step.  `prev` / `next`: plane (t) of the buffer in the previous / next rank,
+// or null.  MIR is a kernel-level template parameter so that the single-GPU kernels stay untouched.
+template <typename YT>
+struct MirrorPlanes {
+    YT* prev;
+    YT* next;
+};
+
+// Peer halo buffers of the two z-neighbours (one (M, Ni, Nj) plane each), or null: see MirrorPlanes.
+template <typename YT>
+struct MirrorBufs {
+    YT* prev;
+    YT* next;
+};
+template <typename YT, typename PT>
+PYTVB_HD MirrorPlanes<YT> mirror_planes(const MirrorBufs<YT>& m, const PT& P, int z, int t) {
+    MirrorPlanes<YT> r;
+    r.prev = (m.prev && z == 0) ? m.prev + (long long)t * P.sT : nullptr;
+    r.next = (m.next && z == P.Nz - 1) ? m.next + (long long)t * P.sT : nullptr;
+    return r;
+}
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, typename YT = T, bool TS = false, bool MIR = false>
+PYTVB_HD T strip_quad_cp_dual(const DualPlane<T, YT>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn, T sig, T lam,
+                              MirrorPlanes<YT> mir = MirrorPlanes<YT>{nullptr, nullptr}) {
     typedef Comp<SCHEME, Z_ON, T_ON> C;
     constexpr int ND = C::ND;
     T y[ND][VEC], d[ND][VEC];
@@ -208,6 +232,12 @@ PYTVB_HD T strip_quad_cp_dual(const DualPlane<T, YT>& pl, const Params<T>& P, in
 #pragma unroll
 #pragma unroll
     for (int k = 0; k < ND; ++k) st_y<T, YT, VEC>(pl.y + (long long)k * P.sC + o, y[k]);
+    if constexpr (MIR && Z_ON) {
+        // the previous rank's adjoint reads my backward-type z slot of my first plane, the next rank's my forward-type
+        // slot of my last plane (see pytvb_DT)
+        if (mir.prev) st_y<T, YT, VEC>(mir.prev + o, y[C::Z_B]);
+        if (mir.next) st_y<T, YT, VEC>(mir.next + o, y[C::Z_F]);
+    }
     return l21;
 }
 
@@ -449,9 +479,9 @@ PYTVB_HD void strip_quad_DT(T* out, const PrimalPlane<T, YT>& pl, const Params<T
 // Primal update at one quad.  VARIANT 0: ROF prox + over-relaxation (aux = xbar); 1: README form (aux = y_f).
 // c1 = 1/(1+tau) (rof) or 1/(1+sigma_A) (readme); c2 = theta or sigma_A.  Returns sum (x_new - x0)^2.
 // `tau` multiplies D^T y: for a normalised half-precision dual the caller passes tau * lam.
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int VARIANT, bool CG = false, typename YT = T, bool TS = false>
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int VARIANT, bool CG = false, typename YT = T, bool TS = false, bool MIR = false>
 PYTVB_HD T strip_quad_cp_primal(T* x, T* aux, const T* x0, const PrimalPlane<T, YT>& pl, const Params<T>& P, int i, int j0, int o, int o_up, int o_dn,
-                                T tau, T c1, T c2, T tau_x0 = T(-1)) {
+                                T tau, T c1, T c2, T tau_x0 = T(-1), MirrorPlanes<T> mir = MirrorPlanes<T>{nullptr, nullptr}) {
     T dty[VEC];
     strip_quad_DT<T, VEC, SCHEME, Z_ON, T_ON, CG, YT, TS>(dty, pl, P, i, j0, o, o_up, o_dn);
     if (tau_x0 < T(0)) tau_x0 = tau;
@@ -479,6 +509,12 @@ PYTVB_HD T strip_quad_cp_primal(T* x, T* aux, const T* x0, const PrimalPlane<T, 
     }
     st_pack<T, VEC>(x + off, xn);
     st_pack<T, VEC>(aux + off, ax);
+    if constexpr (MIR && Z_ON) {
+        // the image the neighbours' next dual pass differentiates: xbar (rof) or x (readme)
+        const Pack<T, VEC>& u = (VARIANT == 0) ? ax : xn;
+        if (mir.prev) st_pack<T, VEC>(mir.prev + o, u);
+        if (mir.next) st_pack<T, VEC>(mir.next + o, u);
+    }
     return fid;
 }
 

@@ -301,7 +301,71 @@ int run(int op, const pytvb_problem* pb, const void* in, void* out, void* out2, 
     return -1;
 }
 
+// peer-memory halo push: the dual / primal strip code with mirror stores (MIR = true), walked like the kernels
+template <typename T> struct MArgs { EArgs<T> e; MirrorBufs<T> mb; };
+template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct EDualM {
+    static int run(const MArgs<T>& m) {
+        const EArgs<T>& a = m.e;
+        double s = 0;
+        for (int z = 0; z < a.P.Nz; ++z)
+            for (int t = 0; t < a.P.M; ++t) {
+                const DualPlane<T> pl = make_dual_plane<T, SCHEME>(a.X, a.out, a.P, z, t);
+                const MirrorPlanes<T> mir = mirror_planes<T>(m.mb, a.P, z, t);
+                for_each_quad_strip(0, 1, 1, a.P.Ni, a.P.Nj, VEC, [&](int, int, int i, int j0, int o, int o_up, int o_dn) {
+                    s += (double)strip_quad_cp_dual<T, VEC, SCHEME, Z, TT, T, false, true>(pl, a.P, i, j0, o, o_up, o_dn, a.c0 * a.P.inv_div, T(1) / a.c1, mir);
+                });
+            }
+        *a.sum = s * (double)a.P.inv_div;
+        return 0;
+    }
+};
+template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct EPrimalM {
+    static int run(const MArgs<T>& m) {
+        const EArgs<T>& a = m.e;
+        double s = 0;
+        const T c1 = T(1) / (T(1) + (a.variant == 0 ? a.c0 : a.c1));
+        for (int z = 0; z < a.P.Nz; ++z)
+            for (int t = 0; t < a.P.M; ++t) {
+                const PrimalPlane<T> pl = make_primal_plane<T, SCHEME, Z, TT>(a.F, a.P, z, t);
+                const MirrorPlanes<T> mir = mirror_planes<T>(m.mb, a.P, z, t);
+                for_each_quad_strip(0, 1, 1, a.P.Ni, a.P.Nj, VEC, [&](int, int, int i, int j0, int o, int o_up, int o_dn) {
+                    if (a.variant == 0)
+                        s += (double)strip_quad_cp_primal<T, VEC, SCHEME, Z, TT, 0, false, T, false, true>(a.out, a.aux, a.x0, pl, a.P, i, j0, o, o_up, o_dn, a.c0, c1, a.c1, T(-1), mir);
+                    else
+                        s += (double)strip_quad_cp_primal<T, VEC, SCHEME, Z, TT, 1, false, T, false, true>(a.out, a.aux, a.x0, pl, a.P, i, j0, o, o_up, o_dn, a.c0, c1, a.c1, T(-1), mir);
+                });
+            }
+        *a.sum = s;
+        return 0;
+    }
+};
+template <typename T>
+int run_mirror(int op, const pytvb_problem* pb, const void* in, void* out, void* aux, const void* x0, const void* lo, const void* hi, void* mp,
+               void* mn, double c0, double c1, int variant, int force_scalar, double* sum) {
+    const Axes ax = axes_of(pb);
+    MArgs<T> m;
+    EArgs<T>& a = m.e;
+    a.P = make_params<T>(pb);
+    a.out = (T*)out; a.out2 = nullptr; a.aux = (T*)aux; a.x0 = (const T*)x0; a.c0 = (T)c0; a.c1 = (T)c1; a.variant = variant; a.sum = sum;
+    a.z_lo = 0; a.nz = a.P.Nz;
+    m.mb = MirrorBufs<T>{(T*)mp, (T*)mn};
+    const int vec = vec_for<T>(pb, force_scalar);
+    if (op == 0) { a.X = ImgView<T>{(const T*)in, (const T*)lo, (const T*)hi, 1}; return dispatch<EDualM, T>(vec, pb->scheme, ax.z_on, ax.t_on, m); }
+    a.F = FieldView<T>{(const T*)in, (const T*)lo, (const T*)hi};
+    return dispatch<EPrimalM, T>(vec, pb->scheme, ax.z_on, ax.t_on, m);
+}
+
 }  // namespace
+
+// op 0: dual pass (in=xbar, out=y), op 1: primal pass (in=y, out=x); mp / mn = the neighbours' halo planes or NULL
+extern "C" int pytvb_emulate_mirror(int op, const pytvb_problem* pb, const void* in, void* out, void* aux, const void* x0, const void* lo,
+                                    const void* hi, void* mp, void* mn, double c0, double c1, int variant, int force_scalar, double* sum) {
+    if (check_problem(pb)) return -1;
+    double dummy = 0;
+    if (!sum) sum = &dummy;
+    return pb->dtype == PYTVB_F32 ? run_mirror<float>(op, pb, in, out, aux, x0, lo, hi, mp, mn, c0, c1, variant, force_scalar, sum)
+                                  : run_mirror<double>(op, pb, in, out, aux, x0, lo, hi, mp, mn, c0, c1, variant, force_scalar, sum);
+}
 
 // op: 0 D (in=x, out=D) | 1 DT (in=p, out=img) | 2 tv (in=x, out=G, out2=norms|NULL, sum=tv)
 //     5 / 6: generation-2 (strip) code of 3 / 4, same arguments;  7 / 8 / 9: generation-2 code of 0 / 1 / 2

@@ -113,6 +113,32 @@ def cp_primal(y, x, aux, x0, scheme, tau, c2, variant, lo=None, hi=None, z_offse
     return _call(4 if GEN == 1 else 6, pb, np.ascontiguousarray(y), x, aux=aux, x0=x0, lo=lo, hi=hi, c0=tau, c1=c2, variant=variant, scalar=scalar)
 
 
+def _call_mirror(op, pb, inp, out, aux, x0, lo, hi, mp, mn, c0, c1, variant, scalar):
+    h = emul()
+    VP = ctypes.c_void_p
+    h.pytvb_emulate_mirror.restype = ctypes.c_int
+    h.pytvb_emulate_mirror.argtypes = [ctypes.c_int, ctypes.POINTER(_lib.Problem)] + [VP] * 8 + [ctypes.c_double, ctypes.c_double, ctypes.c_int,
+                                                                                              ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    s = ctypes.c_double(0.0)
+    rc = h.pytvb_emulate_mirror(op, ctypes.byref(pb), _ptr(inp), _ptr(out), _ptr(aux), _ptr(x0), _ptr(lo), _ptr(hi), _ptr(mp), _ptr(mn), c0, c1,
+                                variant, int(scalar), ctypes.byref(s))
+    assert rc == 0, h.pytvb_emulate_error()
+    return s.value
+
+
+def cp_dual_mirror(xbar, y, scheme, lam, sigma, lo, hi, mirror_prev, mirror_next, z_offset, Nz_global, scalar=False, **w):
+    """Dual pass of one slab that also stores its boundary z-components into the neighbours' halo planes."""
+    pb, keep = _problem(scheme, xbar.dtype, xbar.shape, w.get("reg_z_over_reg", 1.0), w.get("reg_time", 0.0), w.get("mask_static", False),
+                        w.get("factor_reg_static", 0.0), z_offset, Nz_global)
+    return _call_mirror(0, pb, np.ascontiguousarray(xbar), y, None, None, lo, hi, mirror_prev, mirror_next, sigma, 1.0 / lam, 0, scalar)
+
+
+def cp_primal_mirror(y, x, aux, x0, scheme, tau, c2, variant, lo, hi, mirror_prev, mirror_next, z_offset, Nz_global, scalar=False, **w):
+    pb, keep = _problem(scheme, x.dtype, x.shape, w.get("reg_z_over_reg", 1.0), w.get("reg_time", 0.0), w.get("mask_static", False),
+                        w.get("factor_reg_static", 0.0), z_offset, Nz_global)
+    return _call_mirror(1, pb, np.ascontiguousarray(y), x, aux, x0, lo, hi, mirror_prev, mirror_next, tau, c2, variant, scalar)
+
+
 def cp_fused(u, y, x, aux, x0, scheme, lam, sigma, tau, c2, variant, lag=3, scalar=False, ilo=None, ihi=None, flo=None, fhi=None, z_offset=0,
              Nz_global=None, **w):
     """One iteration through the emulated single-launch schedule (generation 3); returns (l21, fid)."""

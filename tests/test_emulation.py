@@ -267,6 +267,63 @@ def test_cp_slabs(scheme, gen):
     assert 0.5 * fid + 0.1 * l21 == pytest.approx(e_ref, rel=1e-12)
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("scheme", SCHEMES)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_cp_peer_halo_push(scheme, variant, dtype):
+    """Multi-GPU schedule without an exchange step: every "rank" (a slab in this process) stores its boundary planes
+    straight into its neighbours' halo buffers from inside the passes (the MIR kernels); three iterations are bitwise
+    equal to the whole-volume strip code.  The slabs run one after the other, a barrier between passes is implied."""
+    rs = np.random.RandomState(11)
+    Nz, M, N = 6, 2, 8
+    bounds = [(0, 1), (1, 4), (4, 6)]          # a one-plane slab too: plane 0 is also its last plane
+    kw = dict(reg_z_over_reg=0.5, reg_time=0.25)
+    Nd = orc.num_components(scheme, Nz, M, 0.5, 0.25)
+    x0 = rs.rand(Nz, M, N, N).astype(dtype)
+    x = x0.copy()
+    aux = x0.copy() if variant == 0 else np.zeros_like(x0)
+    y = np.zeros((Nz, Nd, M, N, N), dtype=dtype)
+    lam, sigma, tau, c2 = 0.1, 0.5, 0.07, (0.9 if variant == 0 else 1.0)
+    # whole volume
+    xw, auxw, yw = x.copy(), aux.copy(), y.copy()
+    saved, em.GEN = em.GEN, 2
+    try:
+        for _ in range(3):
+            em.cp_dual(auxw if variant == 0 else xw, yw, scheme, lam, sigma, **kw)
+            em.cp_primal(yw, xw, auxw, x0, scheme, tau, c2, variant, **kw)
+    finally:
+        em.GEN = saved
+    # slabs with four halo planes each: [img_lo, img_hi, fld_lo, fld_hi]
+    nr = len(bounds)
+    X = [np.ascontiguousarray(x[a:b]) for a, b in bounds]
+    A = [np.ascontiguousarray(aux[a:b]) for a, b in bounds]
+    Y = [np.ascontiguousarray(y[a:b]) for a, b in bounds]
+    X0 = [np.ascontiguousarray(x0[a:b]) for a, b in bounds]
+    H = [np.full((4, M, N, N), np.nan, dtype=dtype) for _ in bounds]
+    need_img_lo, need_img_hi = scheme != "upwind", scheme != "downwind"
+    need_fld_lo, need_fld_hi = scheme != "downwind", scheme != "upwind"
+    U = A if variant == 0 else X
+    for r in range(nr):                        # the one start-up exchange of the image halos
+        if r > 0:
+            H[r][0] = U[r - 1][-1]
+        if r < nr - 1:
+            H[r][1] = U[r + 1][0]
+    for _ in range(3):
+        for r, (a, b) in enumerate(bounds):
+            mp = H[r - 1][3] if (r > 0 and need_fld_hi) else None        # my backward-type z slot -> previous rank's fld_hi
+            mn = H[r + 1][2] if (r < nr - 1 and need_fld_lo) else None   # my forward-type z slot -> next rank's fld_lo
+            em.cp_dual_mirror(U[r], Y[r], scheme, lam, sigma, H[r][0] if (r > 0 and need_img_lo) else None,
+                              H[r][1] if (r < nr - 1 and need_img_hi) else None, mp, mn, a, Nz, **kw)
+        for r, (a, b) in enumerate(bounds):
+            mp = H[r - 1][1] if (r > 0 and need_img_hi) else None        # my first plane -> previous rank's img_hi
+            mn = H[r + 1][0] if (r < nr - 1 and need_img_lo) else None   # my last plane -> next rank's img_lo
+            em.cp_primal_mirror(Y[r], X[r], A[r], X0[r], scheme, tau, c2, variant, H[r][2] if (r > 0 and need_fld_lo) else None,
+                                H[r][3] if (r < nr - 1 and need_fld_hi) else None, mp, mn, a, Nz, **kw)
+    np.testing.assert_array_equal(np.concatenate(X), xw)
+    np.testing.assert_array_equal(np.concatenate(A), auxw)
+    np.testing.assert_array_equal(np.concatenate(Y), yw)
+
+
 def test_central_nz2_intent(gen):
     rs = np.random.RandomState(9)
     x = rs.rand(2, 2, 6, 6)

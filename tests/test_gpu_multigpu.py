@@ -20,8 +20,8 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, scheme, out_dir, overlap):
-    os.environ["PYTVB_OVERLAP"] = overlap
+def _worker(rank, world, port, scheme, out_dir, mode):
+    os.environ["PYTVB_OVERLAP"] = "1" if mode == "overlap" else "0"
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     import pytv_b200
@@ -33,7 +33,9 @@ def _worker(rank, world, port, scheme, out_dir, overlap):
         g = torch.Generator().manual_seed(3)
         x0 = torch.rand(12, 3, 64, 64, generator=g)
         off, cnt = pytv_b200.partition_z(12, world)[rank]
-        s = pytv_b200.CPSolver(x0[off:off + cnt].cuda(), lam=0.1, scheme=scheme, variant="rof", reg_time=0.25, distributed=True)
+        s = pytv_b200.CPSolver(x0[off:off + cnt].cuda(), lam=0.1, scheme=scheme, variant="rof", reg_time=0.25, distributed=True,
+                                comm="p2p" if mode == "p2p" else "nccl")
+        assert (s._peer is not None) == (mode == "p2p")
         energies = []
         for _ in range(5):
             s.step()
@@ -45,14 +47,16 @@ def _worker(rank, world, port, scheme, out_dir, overlap):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("overlap", ["0", "1"], ids=["blocking", "overlap"])
-@pytest.mark.parametrize("scheme", ["hybrid", "central", "upwind"])
-def test_two_gpu_sharded_cp_equals_single_gpu(tmp_path, scheme, overlap):
+@pytest.mark.parametrize("mode", ["blocking", "overlap", "p2p"])
+@pytest.mark.parametrize("scheme", ["hybrid", "central", "upwind", "downwind"])
+def test_two_gpu_sharded_cp_equals_single_gpu(tmp_path, scheme, mode):
+    """mode: NCCL send/recv before each pass | the same hidden behind the interior planes | no exchange at all, the
+    kernels store the boundary planes into the neighbour's halo buffers over NVLink (peer memory)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import pytv_b200
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), scheme, str(tmp_path), overlap), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), scheme, str(tmp_path), mode), nprocs=world, join=True)
     x = np.concatenate([np.load(tmp_path / ("x_%d.npy" % r)) for r in range(world)], axis=0)
     g = torch.Generator().manual_seed(3)
     x0 = torch.rand(12, 3, 64, 64, generator=g)
