@@ -406,7 +406,9 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W, "ms_per_step": t_ms / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config_dict(n_gpus, {"slab_per_gpu": list(shape), "energy_last": energy,
-                                               "halo_comm": "none (one GPU)" if world == 1 else comm}),
+                                               "halo_comm": "none (one GPU)" if world == 1 else
+                                               ("p2p (kernels store boundary planes into the neighbours' halo buffers over NVLink)"
+                                                if solver._peer is not None else "nccl send/recv")}),
                 "roofline": roofline,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": img_bytes * world, "d2h_bytes_per_step": (img_bytes + 16) * world,
                         "ms_per_step": 1e3 * e2e_s / K, "ms_per_step_unpipelined": e2e_sync_ms,
@@ -431,7 +433,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--comm", choices=["nccl", "p2p"], default=os.environ.get("PYTVB_BENCH_COMM", "nccl"),
+    ap.add_argument("--comm", choices=["auto", "nccl", "p2p"], default=os.environ.get("PYTVB_BENCH_COMM", "auto"),
                     help="N > 1: halo planes by NCCL send/recv between the passes, or pushed by the kernels into peer memory")
     ap.add_argument("--slab", type=int, nargs=4, default=None, help="override the per-GPU slab (Nz M Ni Nj); debugging only")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline leg (profiling runs)")

@@ -276,23 +276,37 @@ class CPSolver:
         self.fused = bool(fused) and self.halo is None and hasattr(self.ops, "cp_iter_fused") and self.dual_dtype == dt
         self._fused_ws = self.ops.fused_workspace(self.pb, dev) if self.fused else None
         self.iterations = 0
-        # halo planes.  comm="p2p" (or PYTVB_P2P=1): no exchange step at all - the planes live in symmetric memory and the
-        # passes of the neighbouring ranks store into them (PeerHalos); comm="nccl": send/recv between the passes.
+        # halo planes.  comm="p2p": no exchange step at all - the planes live in symmetric memory and the passes of the
+        # neighbouring ranks store into them (PeerHalos); comm="nccl": send/recv between the passes; "auto" (default,
+        # or PYTVB_COMM): p2p where it can be set up on every rank, else nccl.
         self._img_lo = self._img_hi = self._fld_lo = self._fld_hi = None
         self._peer = None
         if comm is None:
-            comm = "p2p" if os.environ.get("PYTVB_P2P", "0") == "1" else "nccl"
-        if comm not in ("nccl", "p2p"):
-            raise ValueError("comm must be 'nccl' or 'p2p'")
+            comm = os.environ.get("PYTVB_COMM", "auto")
+        if comm not in ("auto", "nccl", "p2p"):
+            raise ValueError("comm must be 'auto', 'nccl' or 'p2p'")
         if self.halo is not None and self.z_on:
             plane = (shape[1], shape[2], shape[3])
             interior_lo, interior_hi = self.halo.prev is not None, self.halo.next is not None
             need_img_lo, need_img_hi = scheme != "upwind", scheme != "downwind"
             need_fld_lo, need_fld_hi = scheme != "downwind", scheme != "upwind"
-            if comm == "p2p":
-                if ops is not None or self._ts is not None or self.dual_dtype != dt or self.overlap:
-                    raise ValueError("comm='p2p' needs the CUDA executor, the blocking schedule, no time_weight and full-precision duals")
-                self._peer = PeerHalos(self.halo, plane, dt, dev)
+            p2p_ok = ops is None and self._ts is None and self.dual_dtype == dt and not self.overlap
+            if comm == "p2p" and not p2p_ok:
+                raise ValueError("comm='p2p' needs the CUDA executor, the blocking schedule, no time_weight and full-precision duals")
+            if comm != "nccl" and p2p_ok:
+                # measured on 8 x B200 (profiles/r01zb_*): 9.86 ms per iteration against 10.18 ms with send/recv (one GPU: 9.60)
+                try:
+                    self._peer = PeerHalos(self.halo, plane, dt, dev)
+                except Exception as exc:              # no symmetric memory here (multi-node group, no P2P, old driver)
+                    if comm == "p2p":
+                        raise
+                    self._peer_error = repr(exc)
+                if comm == "auto":                    # every rank must take the same path
+                    ok = torch.tensor([1 if self._peer is not None else 0], dtype=torch.int32, device=dev)
+                    self.halo.dist.all_reduce(ok, op=self.halo.dist.ReduceOp.MIN, group=self.halo.group)
+                    if int(ok.item()) == 0:
+                        self._peer = None
+            if self._peer is not None:
                 mk = lambda d=dt, slot=0: self._peer.local(slot)
             else:
                 mk = lambda d=dt, slot=0: torch.empty(plane, dtype=d, device=dev)

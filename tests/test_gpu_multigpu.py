@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, scheme, out_dir, mode):
+def _worker(rank, world, port, scheme, out_dir, mode, variant="rof"):
     os.environ["PYTVB_OVERLAP"] = "1" if mode == "overlap" else "0"
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
@@ -33,13 +33,17 @@ def _worker(rank, world, port, scheme, out_dir, mode):
         g = torch.Generator().manual_seed(3)
         x0 = torch.rand(12, 3, 64, 64, generator=g)
         off, cnt = pytv_b200.partition_z(12, world)[rank]
-        s = pytv_b200.CPSolver(x0[off:off + cnt].cuda(), lam=0.1, scheme=scheme, variant="rof", reg_time=0.25, distributed=True,
-                                comm="p2p" if mode == "p2p" else "nccl")
-        assert (s._peer is not None) == (mode == "p2p")
+        s = pytv_b200.CPSolver(x0[off:off + cnt].cuda(), lam=0.1, scheme=scheme, reg_time=0.25, distributed=True,
+                                comm=mode if mode in ("p2p", "auto") else "nccl", variant=variant)
+        if mode != "auto":        # auto: peer memory where the box offers it, NCCL otherwise - the result is the same
+            assert (s._peer is not None) == (mode == "p2p")
         energies = []
         for _ in range(5):
             s.step()
             energies.append(s.energy())
+        if variant == "rof":      # the diagnostics reuse the halo buffers between iterations: iterate on afterwards
+            energies.extend(s.gap())
+            s.step(2)
         np.save(os.path.join(out_dir, "x_%d.npy" % rank), s.result())
         if rank == 0:
             np.save(os.path.join(out_dir, "e.npy"), np.array(energies))
@@ -47,7 +51,7 @@ def _worker(rank, world, port, scheme, out_dir, mode):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["blocking", "overlap", "p2p"])
+@pytest.mark.parametrize("mode", ["blocking", "overlap", "p2p", "auto"])
 @pytest.mark.parametrize("scheme", ["hybrid", "central", "upwind", "downwind"])
 def test_two_gpu_sharded_cp_equals_single_gpu(tmp_path, scheme, mode):
     """mode: NCCL send/recv before each pass | the same hidden behind the interior planes | no exchange at all, the
@@ -65,8 +69,13 @@ def test_two_gpu_sharded_cp_equals_single_gpu(tmp_path, scheme, mode):
     for _ in range(5):
         s.step()
         energies.append(s.energy())
+    energies.extend(s.gap())
+    s.step(2)
     np.testing.assert_array_equal(x, s.result())
-    np.testing.assert_allclose(np.load(tmp_path / "e.npy"), energies, rtol=1e-12)
+    e = np.load(tmp_path / "e.npy")
+    np.testing.assert_allclose(e[:5], energies[:5], rtol=1e-12)
+    np.testing.assert_allclose(e[5:7], energies[5:7], rtol=1e-9)            # primal, dual energy (other summation grouping)
+    assert abs(e[7] - energies[7]) <= 1e-9 * abs(energies[5])
 
 
 def _sharded_worker(rank, world, port, scheme, out_dir):
@@ -119,3 +128,21 @@ def test_two_gpu_sharded_operators_equal_single_gpu(tmp_path, scheme):
     np.testing.assert_array_equal(cat("norms"), n1.cpu().numpy())
     assert parts[0]["scal"][1] == pytest.approx(float(tv1), rel=1e-6)
     assert parts[0]["scal"][0] == pytest.approx(float(pytv.tv_operators_GPU.compute_L21_norm(D1)), rel=1e-6)
+
+
+def test_two_gpu_peer_halo_push_readme_variant(tmp_path):
+    """The README form of the iteration (x, y_f, y_tv) through the peer-memory halo push: pass B pushes x, not xbar."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import pytv_b200
+    mp.spawn(_worker, args=(2, _free_port(), "hybrid", str(tmp_path), "p2p", "readme"), nprocs=2, join=True)
+    x = np.concatenate([np.load(tmp_path / ("x_%d.npy" % r)) for r in range(2)], axis=0)
+    g = torch.Generator().manual_seed(3)
+    x0 = torch.rand(12, 3, 64, 64, generator=g)
+    s = pytv_b200.CPSolver(x0.cuda(), lam=0.1, scheme="hybrid", variant="readme", reg_time=0.25)
+    energies = []
+    for _ in range(5):
+        s.step()
+        energies.append(s.energy())
+    np.testing.assert_array_equal(x, s.result())
+    np.testing.assert_allclose(np.load(tmp_path / "e.npy"), energies, rtol=1e-12)
