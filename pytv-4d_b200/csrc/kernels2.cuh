@@ -14,6 +14,12 @@
 #ifndef PYTVB_PRIMAL_MINB
 #define PYTVB_PRIMAL_MINB 3
 #endif
+#ifndef PYTVB_TVNORM_MINB
+#define PYTVB_TVNORM_MINB 4   // TV sweeps: 64 registers, 4 CTAs per SM (measured against 3 / uncapped, profiles/r01zd_*)
+#endif
+#ifndef PYTVB_TVGRAD_MINB
+#define PYTVB_TVGRAD_MINB 4
+#endif
 
 namespace pytvb {
 
@@ -160,8 +166,9 @@ __global__ void __launch_bounds__(CTA_THREADS) l21_strip_kernel(const T* __restr
 }
 
 // TV sweep 1 (strip form): z range tl.z_lo .. tl.z_lo+tl.nz-1 includes one halo plane per side when present.
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, bool TS = false>
-__global__ void __launch_bounds__(CTA_THREADS) tv_norm_strip_kernel(ImgView<T> X, T* __restrict__ Wz0, T* __restrict__ norms, double* __restrict__ partial,
+// FAC: the time component carries a per-voxel factor (mask_static / weight map); the launcher picks the variant.
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, bool TS = false, bool FAC = true>
+__global__ void __launch_bounds__(CTA_THREADS, PYTVB_TVNORM_MINB) tv_norm_strip_kernel(ImgView<T> X, T* __restrict__ Wz0, T* __restrict__ norms, double* __restrict__ partial,
                                                                     Params<T> P, Tiling tl) {
     const QuadIdx q = decode_quad(tl, (P.Ni + R - 1) / R, VEC);
     T sum = T(0);
@@ -170,22 +177,30 @@ __global__ void __launch_bounds__(CTA_THREADS) tv_norm_strip_kernel(ImgView<T> X
         const long long img = (long long)q.z * P.sZ + (long long)q.t * P.sT;
         const bool own = q.z >= 0 && q.z < P.Nz;
         T* np = (norms && own) ? norms + img : nullptr;
-        for_strip_rows<R>(q, P.Ni, P.Nj, [&](int i, int o, int o_up, int o_dn) {
-            const T v = strip_quad_tv_norm<T, VEC, SCHEME, Z_ON, T_ON, TS>(Wz0 ? Wz0 + img : nullptr, np, pl, P, i, q.j0, o, o_up, o_dn);
-            if (own) sum += v;
-        });
+        if constexpr (SCHEME == CENTRAL) {
+            for_strip_rows<R>(q, P.Ni, P.Nj, [&](int i, int o, int o_up, int o_dn) {
+                const T v = strip_quad_tv_norm<T, VEC, SCHEME, Z_ON, T_ON, TS>(Wz0 ? Wz0 + img : nullptr, np, pl, P, i, q.j0, o, o_up, o_dn);
+                if (own) sum += v;
+            });
+        } else {
+            const T v = strip_rows_tv_norm<T, VEC, SCHEME, Z_ON, T_ON, R, TS, FAC>(Wz0 ? Wz0 + img : nullptr, np, pl, P, q.i * R, q.j0);
+            if (own) sum = v;
+        }
     }
     const double bs = block_sum((double)sum);
     if (threadIdx.x == 0) partial[blockIdx.x] = bs;
 }
 
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, bool TS = false>
-__global__ void __launch_bounds__(CTA_THREADS) tv_grad_strip_kernel(ImgView<T> X, ImgView<T> W, T* __restrict__ G, Params<T> P, Tiling tl) {
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, bool TS = false, bool FAC = true>
+__global__ void __launch_bounds__(CTA_THREADS, PYTVB_TVGRAD_MINB) tv_grad_strip_kernel(ImgView<T> X, ImgView<T> W, T* __restrict__ G, Params<T> P, Tiling tl) {
     const QuadIdx q = decode_quad(tl, (P.Ni + R - 1) / R, VEC);
     if (!q.active) return;
     const GradPlane<T> pl = make_grad_plane<T, SCHEME>(X, W, P, q.z, q.t);
     T* gp = G + (long long)q.z * P.sZ + (long long)q.t * P.sT;
-    for_strip_rows<R>(q, P.Ni, P.Nj, [&](int i, int o, int, int) { strip_quad_G<T, VEC, SCHEME, Z_ON, T_ON, TS>(gp, pl, P, i, q.j0, o); });
+    if constexpr (SCHEME == CENTRAL)
+        for_strip_rows<R>(q, P.Ni, P.Nj, [&](int i, int o, int, int) { strip_quad_G<T, VEC, SCHEME, Z_ON, T_ON, TS>(gp, pl, P, i, q.j0, o); });
+    else
+        strip_rows_G<T, VEC, SCHEME, Z_ON, T_ON, R, TS, FAC>(gp, pl, P, q.i * R, q.j0, tl.TW >= 32);
 }
 
 }  // namespace pytvb

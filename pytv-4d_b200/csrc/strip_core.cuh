@@ -653,4 +653,286 @@ PYTVB_HD void strip_quad_G(T* g_plane, const GradPlane<T>& pl, const Params<T>& 
     strip_quad_G_impl<T, VEC, SCHEME, Z_ON, T_ON, TS && T_ON>(g_plane, pl, P, i, j0, o);
 }
 
+// ------------------------------------------------------------------------------------------------
+// TV sweeps, row-marching form (one-sided and hybrid schemes; the centred scheme keeps the per-row form above).
+// A thread walks down the R rows of its strip and keeps the current row, and the row difference (sweep 1) or row term
+// (sweep 2) it shares with the next row, in registers: one new row load per array and row instead of three, every
+// difference / product that two neighbouring voxels share is computed once, and the axis weights are applied to sums of
+// squares instead of to each difference.  Both sweeps were instruction-issue bound (260 instructions per quad each,
+// profiles/r01f_*), so the instruction count is what this form cuts.
+
+// S(w_k, w_{k+1}) of the sub-gradient term between voxels k and k+1 along one axis:
+//   G_axis(k) = term(k-1) - term(k),  term(k) = (x_{k+1} - x_k) * S(w_k, w_{k+1})
+// (upwind: w_k, downwind: w_{k+1}, hybrid: the sum; clamped neighbours make the terms across the boundary vanish).
+template <typename T, int SCHEME>
+PYTVB_HD T pair_w(T wk, T wk1) {
+    return SCHEME == UPWIND ? wk : (SCHEME == DOWNWIND ? wk1 : wk + wk1);
+}
+
+// Elements just left / right of this thread's quad in its row (clamped at the image edge).  On the device, when the warp
+// covers 32 consecutive quads of one row (`wrow`), they come from the neighbouring lanes' registers: the scalar loads they
+// replace cost the L1 as many wavefronts as a 128-bit load, and the TV sweeps are L1-bound.  The lanes at the warp's
+// ends - and every lane when the warp spans several rows - load them.  `m`: the lanes that execute the sweep together.
+template <typename T>
+PYTVB_HD void row_neighbours(T& l, T& r, const T* row_o, T first, T last, bool has_l, bool has_r, int vec, bool wrow, unsigned m,
+                             bool need_l, bool need_r) {
+#if defined(__CUDA_ARCH__)
+    const int lane = threadIdx.x & 31;
+    const T sl = need_l ? __shfl_up_sync(m, last, 1) : first, sr = need_r ? __shfl_down_sync(m, first, 1) : last;
+    const bool use_l = wrow && lane > 0, use_r = wrow && lane < 31 && has_r;
+    l = !need_l ? first : (use_l ? sl : (has_l ? row_o[-1] : first));
+    r = !need_r ? last : (use_r ? sr : (has_r ? row_o[vec] : last));
+#else
+    (void)wrow; (void)m;
+    l = (need_l && has_l) ? row_o[-1] : first;
+    r = (need_r && has_r) ? row_o[vec] : last;
+#endif
+}
+PYTVB_HD unsigned sweep_lanes() {
+#if defined(__CUDA_ARCH__)
+    return __activemask();
+#else
+    return 1u;
+#endif
+}
+
+// 1/sqrt(s), the norm and its inverse for sweep 1.  float on the device: one MUFU.RSQ without the denormal fix-up of
+// rsqrtf (5 instructions per voxel less); a sum of squares below FLT_MIN (all differences < 1.1e-19) counts as zero.
+template <typename T>
+PYTVB_HD void norm_finish(T s, const Params<T>& P, T& nr, T& w, bool& pos) {
+    const T rs = fast_rsqrt(s);                 // inf for s == 0
+    pos = s > T(0);
+    nr = pos ? s * rs * P.inv_div : T(0);
+    w = pos ? rs * P.div : T(0);
+}
+#if defined(__CUDA_ARCH__)
+template <>
+__device__ __forceinline__ void norm_finish<float>(float s, const Params<float>& P, float& nr, float& w, bool& pos) {
+    float rs;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(fmaxf(s, 1.17549435e-38f)));
+    pos = s >= 1.17549435e-38f;
+    nr = pos ? s * rs * P.inv_div : 0.0f;
+    w = pos ? rs * P.div : 0.0f;
+}
+#endif
+
+// Sweep 1 over rows i0 .. i0+R-1 of one quad column: w = 1/|D x| (0 where the norm is 0) into `w_plane`, optionally
+// the norms (inf where 0) into `n_plane`; returns the sum of the norms.  FAC: the time component carries a per-voxel
+// factor (mask_static or a weight map); without it the weight is uniform.  Rows past the image (last strip) recompute
+// the last row and are not stored: the row loop has no branches.
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, bool TS, bool FAC>
+PYTVB_HD T strip_rows_tv_norm_impl(T* w_plane, T* n_plane, const DualPlane<T>& pl, const Params<T>& P, int i0, int j0) {
+    static_assert(SCHEME != CENTRAL, "row-marching sweeps are for the one-sided and hybrid schemes");
+    typedef Comp<SCHEME, Z_ON, T_ON> C;
+    constexpr bool FWD = C::NEED_FWD, BWD = C::NEED_BWD;
+    const int Nj = P.Nj, Ni = P.Ni;
+    int o = i0 * Nj + j0;
+    T xc[VEC], db[VEC];            // row i; x_i - x_{i-1}
+    ld_into<T, VEC>(xc, pl.c + o);
+    if (BWD) {
+        T up[VEC];
+        ld_into<T, VEC>(up, pl.c + (i0 > 0 ? o - Nj : o));
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) db[e] = xc[e] - up[e];
+    }
+    const bool has_l = j0 > 0, has_r = j0 + VEC < Nj;
+    const T rz2 = P.srz * P.srz, rt2 = P.srt * P.srt;
+    T sum = T(0);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = i0 + r;
+        const bool live = r == 0 || i < Ni;
+        const int on = i < Ni - 1 ? o + Nj : o;
+        T xn[VEC], df[VEC], s[VEC];
+        if (FWD || r + 1 < R) {
+            ld_into<T, VEC>(xn, pl.c + on);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) df[e] = xn[e] - xc[e];
+        }
+        // (plain loads here: with the lane exchange of sweep 2 this sweep measured 20 % slower - it is not L1-bound)
+        const T cl = (BWD && has_l) ? pl.c[o - 1] : xc[0], cr = (FWD && has_r) ? pl.c[o + VEC] : xc[VEC - 1];
+        if (FWD) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const T jf = (e + 1 < VEC ? xc[e + 1 < VEC ? e + 1 : e] : cr) - xc[e];
+                s[e] = df[e] * df[e];
+                s[e] += jf * jf;
+            }
+        }
+        if (BWD) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const T jb = xc[e] - (e > 0 ? xc[e > 0 ? e - 1 : 0] : cl);
+                if (FWD) s[e] += db[e] * db[e]; else s[e] = db[e] * db[e];
+                s[e] += jb * jb;
+            }
+        }
+        if (Z_ON) {
+            T q[VEC];
+            if (FWD) {
+                T zp[VEC];
+                ld_into<T, VEC>(zp, pl.zp + o);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) { const T d = zp[e] - xc[e]; q[e] = d * d; }
+            }
+            if (BWD) {
+                T zm[VEC];
+                ld_into<T, VEC>(zm, pl.zm + o);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) { const T d = xc[e] - zm[e]; if (FWD) q[e] += d * d; else q[e] = d * d; }
+            }
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) s[e] += rz2 * q[e];
+        }
+        if (T_ON) {
+            T q[VEC];
+            if (FWD) {
+                T tp[VEC];
+                ld_into<T, VEC>(tp, pl.tp + o);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) { const T d = tp[e] - xc[e]; q[e] = d * d; }
+            }
+            if (BWD) {
+                T tm[VEC];
+                ld_into<T, VEC>(tm, pl.tm + o);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) { const T d = xc[e] - tm[e]; if (FWD) q[e] += d * d; else q[e] = d * d; }
+            }
+            if constexpr (FAC) {
+                T fac[VEC];
+                const int il = i < Ni ? i : Ni - 1;
+                if constexpr (TS) time_factor<T, VEC>(fac, P, pl.ts, il, j0, o); else static_factor<T, VEC>(fac, P, il, j0);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) { const T wt = P.srt * fac[e]; s[e] += (wt * wt) * q[e]; }
+            } else {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) s[e] += rt2 * q[e];
+            }
+        }
+        Pack<T, VEC> w, n;
+        T rowsum = T(0);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            T nr; bool pos;
+            norm_finish<T>(s[e], P, nr, w.v[e], pos);
+            n.v[e] = pos ? nr : T(INFINITY);
+            rowsum += nr;
+        }
+        if (live) {
+            sum += rowsum;
+            if (w_plane) st_pack<T, VEC>(w_plane + o, w);
+            if (n_plane) st_pack<T, VEC>(n_plane + o, n);
+        }
+        if (r + 1 < R) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) { if (BWD) db[e] = df[e]; xc[e] = xn[e]; }
+            o = on;
+        }
+    }
+    return sum;
+}
+// FAC must be true when the problem has a mask_static or a weight map (the launcher decides; TS implies FAC).
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, bool TS = false, bool FAC = true>
+PYTVB_HD T strip_rows_tv_norm(T* w_plane, T* n_plane, const DualPlane<T>& pl, const Params<T>& P, int i0, int j0) {
+    return strip_rows_tv_norm_impl<T, VEC, SCHEME, Z_ON, T_ON, R, TS && T_ON, (FAC || TS) && T_ON>(w_plane, n_plane, pl, P, i0, j0);
+}
+
+#ifndef PYTVB_TVGRAD_UNROLL
+#define PYTVB_TVGRAD_UNROLL 1    // row loop of sweep 2 stays a loop: unrolled, the compiler hoists the ten row loads of every row and needs 200+ registers
+#endif
+// Sweep 2 over rows i0 .. i0+R-1 of one quad column: the sub-gradient from x and w.
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, bool TS, bool FAC>
+PYTVB_HD void strip_rows_G_impl(T* g_plane, const GradPlane<T>& pl, const Params<T>& P, int i0, int j0, bool wrow) {
+    const unsigned lanes = sweep_lanes();
+    static_assert(SCHEME != CENTRAL, "row-marching sweeps are for the one-sided and hybrid schemes");
+    const int Nj = P.Nj, Ni = P.Ni;
+    int o = i0 * Nj + j0;
+    T xc[VEC], wc[VEC], ti[VEC];     // row i of x and w; the row term between rows i-1 and i
+    ld_into<T, VEC>(xc, pl.x + o);
+    ld_into<T, VEC>(wc, pl.w + o);
+    {
+        T xu[VEC], wu[VEC];
+        const int ou = i0 > 0 ? o - Nj : o;
+        ld_into<T, VEC>(xu, pl.x + ou);
+        ld_into<T, VEC>(wu, pl.w + ou);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) ti[e] = (xc[e] - xu[e]) * pair_w<T, SCHEME>(wu[e], wc[e]);
+    }
+    const bool has_l = j0 > 0, has_r = j0 + VEC < Nj;
+    const T k2 = P.inv_div * P.inv_div;
+    constexpr int UNR = PYTVB_TVGRAD_UNROLL;
+#pragma unroll(UNR)
+    for (int r = 0; r < R; ++r) {
+        const int i = i0 + r;
+        const bool live = r == 0 || i < Ni;
+        const int on = i < Ni - 1 ? o + Nj : o;
+        T xn[VEC], wn[VEC], g[VEC];
+        ld_into<T, VEC>(xn, pl.x + on);
+        ld_into<T, VEC>(wn, pl.w + on);
+        // ---- rows
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const T tn = (xn[e] - xc[e]) * pair_w<T, SCHEME>(wc[e], wn[e]);
+            g[e] = ti[e] - tn;
+            ti[e] = tn;
+        }
+        // ---- columns: VEC + 1 terms for VEC voxels
+        {
+            T xl, xr, wl, wr;
+            row_neighbours<T>(xl, xr, pl.x + o, xc[0], xc[VEC - 1], has_l, has_r, VEC, wrow, lanes, true, true);
+            row_neighbours<T>(wl, wr, pl.w + o, wc[0], wc[VEC - 1], has_l, has_r, VEC, wrow, lanes, true, true);
+            T tj = (xc[0] - xl) * pair_w<T, SCHEME>(wl, wc[0]);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const T xe = e + 1 < VEC ? xc[e + 1 < VEC ? e + 1 : e] : xr, we = e + 1 < VEC ? wc[e + 1 < VEC ? e + 1 : e] : wr;
+                const T tn = (xe - xc[e]) * pair_w<T, SCHEME>(wc[e], we);
+                g[e] += tj - tn;
+                tj = tn;
+            }
+        }
+        if (Z_ON) {
+            T xm[VEC], xp[VEC], wm[VEC], wp[VEC];
+            ld_into<T, VEC>(xm, pl.xzm + o);  ld_into<T, VEC>(xp, pl.xzp + o);
+            ld_into<T, VEC>(wm, pl.wzm + o);  ld_into<T, VEC>(wp, pl.wzp + o);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const T v = (xc[e] - xm[e]) * pair_w<T, SCHEME>(wm[e], wc[e]) - (xp[e] - xc[e]) * pair_w<T, SCHEME>(wc[e], wp[e]);
+                g[e] += P.srz * v;
+            }
+        }
+        if (T_ON) {
+            T xm[VEC], xp[VEC], wm[VEC], wp[VEC], wq[VEC];
+            ld_into<T, VEC>(xm, pl.xtm + o);  ld_into<T, VEC>(xp, pl.xtp + o);
+            ld_into<T, VEC>(wm, pl.wtm + o);  ld_into<T, VEC>(wp, pl.wtp + o);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) wq[e] = wc[e];
+            if constexpr (TS) {   // along t the inverse norms travel with their voxel's scale (see strip_quad_G_impl)
+                scale_by<T, VEC>(wm, pl.ts_m, o); scale_by<T, VEC>(wq, pl.ts_c, o); scale_by<T, VEC>(wp, pl.ts_p, o);
+            }
+            T fac[VEC];
+            if constexpr (FAC) static_factor<T, VEC>(fac, P, i < Ni ? i : Ni - 1, j0);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const T v = (xc[e] - xm[e]) * pair_w<T, SCHEME>(wm[e], wq[e]) - (xp[e] - xc[e]) * pair_w<T, SCHEME>(wq[e], wp[e]);
+                if constexpr (FAC) g[e] += (P.srt * v) * fac[e]; else g[e] += P.srt * v;
+            }
+        }
+        if (live) {
+            Pack<T, VEC> pk;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) pk.v[e] = g[e] * k2;
+            st_pack<T, VEC>(g_plane + o, pk);
+        }
+        if (r + 1 < R) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) { xc[e] = xn[e]; wc[e] = wn[e]; }
+            o = on;
+        }
+    }
+}
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, bool TS = false, bool FAC = true>
+PYTVB_HD void strip_rows_G(T* g_plane, const GradPlane<T>& pl, const Params<T>& P, int i0, int j0, bool wrow = false) {
+    strip_rows_G_impl<T, VEC, SCHEME, Z_ON, T_ON, R, TS && T_ON, FAC && T_ON>(g_plane, pl, P, i0, j0, wrow);
+}
+
 }  // namespace pytvb

@@ -5,7 +5,7 @@
 #include "kernels2.cuh"
 
 #ifndef PYTVB_STRIP_R
-#define PYTVB_STRIP_R 4
+#define PYTVB_STRIP_R 8
 #endif
 
 using namespace pytvb;
@@ -29,14 +29,19 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchTv {
                 constexpr int R = PYTVB_STRIP_R;
                 const Tiling t1 = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.nz, VEC, a.z_lo);
                 if (int rc = check_grid(t1)) return rc;
-                if (TT && a.P.tscale) tv_norm_strip_kernel<T, VEC, SCHEME, Z, TT, R, TT><<<(unsigned)t1.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.Wz0, a.norms, a.partial, a.P, t1);
-                else tv_norm_strip_kernel<T, VEC, SCHEME, Z, TT, R, false><<<(unsigned)t1.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.Wz0, a.norms, a.partial, a.P, t1);
+                // kernel variants: weight map (TS) | mask_static only (FAC) | uniform time weight; the centred scheme has no FAC form
+                constexpr bool CEN = SCHEME == CENTRAL;
+                const bool fac = CEN || (TT && a.P.mask_static);
+                if (TT && a.P.tscale) tv_norm_strip_kernel<T, VEC, SCHEME, Z, TT, R, TT, true><<<(unsigned)t1.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.Wz0, a.norms, a.partial, a.P, t1);
+                else if (fac) tv_norm_strip_kernel<T, VEC, SCHEME, Z, TT, R, false, true><<<(unsigned)t1.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.Wz0, a.norms, a.partial, a.P, t1);
+                else tv_norm_strip_kernel<T, VEC, SCHEME, Z, TT, R, false, CEN><<<(unsigned)t1.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.Wz0, a.norms, a.partial, a.P, t1);
                 count_launches(1);
                 PYTVB_CUDA(cudaGetLastError());
                 *a.nblocks_out = t1.nblocks;
                 const Tiling t2 = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.P.Nz, VEC);
-                if (TT && a.P.tscale) tv_grad_strip_kernel<T, VEC, SCHEME, Z, TT, R, TT><<<(unsigned)t2.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.W, a.G, a.P, t2);
-                else tv_grad_strip_kernel<T, VEC, SCHEME, Z, TT, R, false><<<(unsigned)t2.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.W, a.G, a.P, t2);
+                if (TT && a.P.tscale) tv_grad_strip_kernel<T, VEC, SCHEME, Z, TT, R, TT, true><<<(unsigned)t2.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.W, a.G, a.P, t2);
+                else if (fac) tv_grad_strip_kernel<T, VEC, SCHEME, Z, TT, R, false, true><<<(unsigned)t2.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.W, a.G, a.P, t2);
+                else tv_grad_strip_kernel<T, VEC, SCHEME, Z, TT, R, false, CEN><<<(unsigned)t2.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.W, a.G, a.P, t2);
                 count_launches(1);
                 PYTVB_CUDA(cudaGetLastError());
                 return PYTVB_OK;
@@ -93,8 +98,11 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchTvVal {
         constexpr int R = PYTVB_STRIP_R;
         const Tiling tl = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.P.Nz, VEC);
         if (int rc = check_grid(tl)) return rc;
-        if (TT && a.P.tscale) tv_norm_strip_kernel<T, VEC, SCHEME, Z, TT, R, TT><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.X, (T*)nullptr, (T*)nullptr, a.partial, a.P, tl);
-        else tv_norm_strip_kernel<T, VEC, SCHEME, Z, TT, R, false><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.X, (T*)nullptr, (T*)nullptr, a.partial, a.P, tl);
+        constexpr bool CEN = SCHEME == CENTRAL;
+        const bool fac = CEN || (TT && a.P.mask_static);
+        if (TT && a.P.tscale) tv_norm_strip_kernel<T, VEC, SCHEME, Z, TT, R, TT, true><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.X, (T*)nullptr, (T*)nullptr, a.partial, a.P, tl);
+        else if (fac) tv_norm_strip_kernel<T, VEC, SCHEME, Z, TT, R, false, true><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.X, (T*)nullptr, (T*)nullptr, a.partial, a.P, tl);
+        else tv_norm_strip_kernel<T, VEC, SCHEME, Z, TT, R, false, CEN><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.X, (T*)nullptr, (T*)nullptr, a.partial, a.P, tl);
         count_launches(1);
         PYTVB_CUDA(cudaGetLastError());
         *a.nb = tl.nblocks;

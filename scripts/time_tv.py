@@ -4,7 +4,7 @@ import pytv_b200 as pytv
 shape = (128, 4, 1024, 1024)
 torch.manual_seed(0)
 x = torch.rand(shape, device="cuda")
-for scheme in ("hybrid", "upwind", "central"):
+for scheme in (sys.argv[1:] or ("hybrid", "upwind", "central")):
     f = getattr(pytv.tv_GPU, "tv_" + scheme)
     for _ in range(3): f(x, return_pytorch_tensor=True, reg_time=2**-5)
     ts = []
