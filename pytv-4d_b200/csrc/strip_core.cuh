@@ -716,6 +716,9 @@ __device__ __forceinline__ void norm_finish<float>(float s, const Params<float>&
 }
 #endif
 
+#ifndef PYTVB_TVNORM_UNROLL
+#define PYTVB_TVNORM_UNROLL 64   // row loop of sweep 1: fully unrolled
+#endif
 // Sweep 1 over rows i0 .. i0+R-1 of one quad column: w = 1/|D x| (0 where the norm is 0) into `w_plane`, optionally
 // the norms (inf where 0) into `n_plane`; returns the sum of the norms.  FAC: the time component carries a per-voxel
 // factor (mask_static or a weight map); without it the weight is uniform.  Rows past the image (last strip) recompute
@@ -738,7 +741,8 @@ PYTVB_HD T strip_rows_tv_norm_impl(T* w_plane, T* n_plane, const DualPlane<T>& p
     const bool has_l = j0 > 0, has_r = j0 + VEC < Nj;
     const T rz2 = P.srz * P.srz, rt2 = P.srt * P.srt;
     T sum = T(0);
-#pragma unroll
+    constexpr int UNR = PYTVB_TVNORM_UNROLL;
+#pragma unroll(UNR)
     for (int r = 0; r < R; ++r) {
         const int i = i0 + r;
         const bool live = r == 0 || i < Ni;

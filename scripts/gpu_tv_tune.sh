@@ -1,9 +1,8 @@
 #!/bin/bash
-# TV sweeps: parity on the device, then per-kernel times of the tuning variants (C4 slab, hybrid / upwind).
+# TV sweeps: per-kernel times of tuning variants (C4 slab, hybrid); variant libraries are selected with PYTVB_LIB_PATH.
 mkdir -p gpurun_out/tvtune
 OUT=gpurun_out/tvtune
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_large.py -q -x -p no:cacheprovider 2>&1 | tail -4 | tee $OUT/pytest.log
-for tag in default; do
+for tag in ${TAGS:-default}; do
   if [ $tag = default ]; then unset PYTVB_LIB_PATH; else export PYTVB_LIB_PATH=$PWD/pytv-4d_b200/csrc/libpytv_b200_$tag.so; fi
   timeout 300 python scripts/time_tv.py hybrid upwind 2>&1 | grep "tv " | sed "s/^/$tag: /" | tee -a $OUT/times.txt
   timeout 300 ncu --metrics gpu__time_duration.sum,launch__registers_per_thread,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:'tv_(norm|grad)_strip' -s 4 -c 2 --csv --log-file $OUT/ncu_$tag.csv python scripts/time_tv.py hybrid > /dev/null 2>&1
