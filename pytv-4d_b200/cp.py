@@ -188,6 +188,11 @@ class CPSolver:
     x0 : (Nz_local, M, Ni, Nj) numpy array or tensor - the noisy data of this rank's slab.
     distributed : True to shard over torch.distributed's default group (or pass `group`); the slab position is
                   derived from the rank with `partition_z` unless z_offset / Nz_global are given.
+    comm : how the one-plane halos travel between z-neighbours.  "p2p": the pass kernels store their boundary planes
+           straight into the neighbour's halo buffers (symmetric memory over NVLink, one node), a device-side barrier
+           separates the passes; "nccl": batched isend/irecv before each pass; "auto" (default, or the environment
+           variable PYTVB_COMM): p2p where every rank can set it up, else nccl.  Half-precision duals, time_weight and
+           injected executors always use nccl.
     """
 
     def __init__(self, x0, lam, scheme="hybrid", variant="rof", sigma=0.5, tau=None, theta=1.0, sigma_A=1.0, reg_z_over_reg=1.0,
