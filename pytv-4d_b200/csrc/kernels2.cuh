@@ -178,10 +178,8 @@ __global__ void __launch_bounds__(CTA_THREADS, PYTVB_TVNORM_MINB) tv_norm_strip_
         const bool own = q.z >= 0 && q.z < P.Nz;
         T* np = (norms && own) ? norms + img : nullptr;
         if constexpr (SCHEME == CENTRAL) {
-            for_strip_rows<R>(q, P.Ni, P.Nj, [&](int i, int o, int o_up, int o_dn) {
-                const T v = strip_quad_tv_norm<T, VEC, SCHEME, Z_ON, T_ON, TS>(Wz0 ? Wz0 + img : nullptr, np, pl, P, i, q.j0, o, o_up, o_dn);
-                if (own) sum += v;
-            });
+            const T v = strip_rows_tv_norm_central<T, VEC, Z_ON, T_ON, R, TS && T_ON, T_ON>(Wz0 ? Wz0 + img : nullptr, np, pl, P, q.i * R, q.j0);
+            if (own) sum = v;
         } else {
             const T v = strip_rows_tv_norm<T, VEC, SCHEME, Z_ON, T_ON, R, TS, FAC>(Wz0 ? Wz0 + img : nullptr, np, pl, P, q.i * R, q.j0);
             if (own) sum = v;
@@ -198,7 +196,7 @@ __global__ void __launch_bounds__(CTA_THREADS, PYTVB_TVGRAD_MINB) tv_grad_strip_
     const GradPlane<T> pl = make_grad_plane<T, SCHEME>(X, W, P, q.z, q.t);
     T* gp = G + (long long)q.z * P.sZ + (long long)q.t * P.sT;
     if constexpr (SCHEME == CENTRAL)
-        for_strip_rows<R>(q, P.Ni, P.Nj, [&](int i, int o, int, int) { strip_quad_G<T, VEC, SCHEME, Z_ON, T_ON, TS>(gp, pl, P, i, q.j0, o); });
+        strip_rows_G_central<T, VEC, Z_ON, T_ON, R, TS>(gp, pl, P, q.i * R, q.j0);
     else
         strip_rows_G<T, VEC, SCHEME, Z_ON, T_ON, R, TS, FAC>(gp, pl, P, q.i * R, q.j0, tl.TW >= 32);
 }

@@ -575,8 +575,9 @@ PYTVB_HD T strip_g_axis(bool fallback, T a, T b, T xm2, T xm, T xc, T xp, T xp2,
     return a * ((xc - xm2) * wm) - b * ((xp2 - xc) * wp);
 }
 
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, bool TS>
-PYTVB_HD void strip_quad_G_impl(T* g_plane, const GradPlane<T>& pl, const Params<T>& P, int i, int j0, int o) {
+// ROWS = false: the row part of the sub-gradient is supplied by the caller in `g_rows` (row-marching form, below).
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, bool TS, bool ROWS = true>
+PYTVB_HD void strip_quad_G_impl(T* g_plane, const GradPlane<T>& pl, const Params<T>& P, int i, int j0, int o, const T* g_rows = nullptr) {
     constexpr bool CEN = (SCHEME == CENTRAL);
     const int Nj = P.Nj;
     const int o_up = i > 0 ? o - Nj : o, o_dn = i < P.Ni - 1 ? o + Nj : o;
@@ -598,7 +599,7 @@ PYTVB_HD void strip_quad_G_impl(T* g_plane, const GradPlane<T>& pl, const Params
         g[e] = strip_g_axis<T, SCHEME>(false, a, b, xr[e], xr[e + 1], xr[e + 2], xr[e + 3], xr[e + 4], wr[e], wr[e + 1], wr[e + 2]);
     }
     // ---- rows
-    {
+    if constexpr (ROWS) {
         T xm[VEC], xp[VEC], wm[VEC], wp[VEC], xm2[VEC], xp2[VEC];
         ld_into<T, VEC>(xm, pl.x + o_up);  ld_into<T, VEC>(xp, pl.x + o_dn);
         ld_into<T, VEC>(wm, pl.w + o_up);  ld_into<T, VEC>(wp, pl.w + o_dn);
@@ -612,6 +613,9 @@ PYTVB_HD void strip_quad_G_impl(T* g_plane, const GradPlane<T>& pl, const Params
 #pragma unroll
         for (int e = 0; e < VEC; ++e)
             g[e] += strip_g_axis<T, SCHEME>(false, a, b, CEN ? xm2[e] : T(0), xm[e], xr[e + 2], xp[e], CEN ? xp2[e] : T(0), wm[e], wr[e + 1], wp[e]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) g[e] += g_rows[e];
     }
     if (Z_ON) {
         T xm[VEC], xp[VEC], wm[VEC], wp[VEC], xm2[VEC], xp2[VEC];
@@ -937,6 +941,130 @@ PYTVB_HD void strip_rows_G_impl(T* g_plane, const GradPlane<T>& pl, const Params
 template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, bool TS = false, bool FAC = true>
 PYTVB_HD void strip_rows_G(T* g_plane, const GradPlane<T>& pl, const Params<T>& P, int i0, int j0, bool wrow = false) {
     strip_rows_G_impl<T, VEC, SCHEME, Z_ON, T_ON, R, TS && T_ON, FAC && T_ON>(g_plane, pl, P, i0, j0, wrow);
+}
+
+// ---- centred scheme, row-marching form.  Rows only: the centred differences along the rows come from a rolling window
+// of registers; columns, z and t keep the per-row code.
+// Sweep 1.
+template <typename T, int VEC, bool Z_ON, bool T_ON, int R, bool TS, bool FAC>
+PYTVB_HD T strip_rows_tv_norm_central(T* w_plane, T* n_plane, const DualPlane<T>& pl, const Params<T>& P, int i0, int j0) {
+    const int Nj = P.Nj, Ni = P.Ni;
+    int o = i0 * Nj + j0;
+    T xu[VEC], xc[VEC];            // rows i-1 (clamped) and i
+    ld_into<T, VEC>(xc, pl.c + o);
+    ld_into<T, VEC>(xu, pl.c + (i0 > 0 ? o - Nj : o));
+    const bool has_l = j0 > 0, has_r = j0 + VEC < Nj;
+    const T wz = P.srz * pl.fz, wz2 = wz * wz, wtu = P.srt * pl.ft, wt2u = wtu * wtu;
+    T sum = T(0);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = i0 + r;
+        const bool live = r == 0 || i < Ni;
+        const int on = i < Ni - 1 ? o + Nj : o;
+        T xn[VEC], s[VEC];
+        ld_into<T, VEC>(xn, pl.c + on);
+        const T fi = (i > 0 && i < Ni - 1) ? T(1) : T(0);
+        const T cl = has_l ? pl.c[o - 1] : xc[0], cr = has_r ? pl.c[o + VEC] : xc[VEC - 1];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const int j = j0 + e;
+            const T fj = (j > 0 && j < Nj - 1) ? T(1) : T(0);
+            const T di = fi * (xn[e] - xu[e]);
+            const T dj = fj * ((e + 1 < VEC ? xc[e + 1 < VEC ? e + 1 : e] : cr) - (e > 0 ? xc[e > 0 ? e - 1 : 0] : cl));
+            s[e] = di * di;
+            s[e] += dj * dj;
+        }
+        if (Z_ON) {
+            T zp[VEC], zm[VEC];
+            ld_into<T, VEC>(zp, pl.zp + o);
+            ld_into<T, VEC>(zm, pl.zm + o);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) { const T d = zp[e] - zm[e]; s[e] += wz2 * (d * d); }
+        }
+        if (T_ON) {
+            T tp[VEC], tm[VEC];
+            ld_into<T, VEC>(tp, pl.tp + o);
+            ld_into<T, VEC>(tm, pl.tm + o);
+            if constexpr (FAC) {
+                T fac[VEC];
+                const int il = i < Ni ? i : Ni - 1;
+                if constexpr (TS) time_factor<T, VEC>(fac, P, pl.ts, il, j0, o); else static_factor<T, VEC>(fac, P, il, j0);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) { const T d = tp[e] - tm[e], wt = wtu * fac[e]; s[e] += (wt * wt) * (d * d); }
+            } else {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) { const T d = tp[e] - tm[e]; s[e] += wt2u * (d * d); }
+            }
+        }
+        Pack<T, VEC> w, n;
+        T rowsum = T(0);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            T nr; bool pos;
+            norm_finish<T>(s[e], P, nr, w.v[e], pos);
+            n.v[e] = pos ? nr : T(INFINITY);
+            rowsum += nr;
+        }
+        if (live) {
+            sum += rowsum;
+            if (w_plane) st_pack<T, VEC>(w_plane + o, w);
+            if (n_plane) st_pack<T, VEC>(n_plane + o, n);
+        }
+        if (r + 1 < R) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) { xu[e] = xc[e]; xc[e] = xn[e]; }
+            o = on;
+        }
+    }
+    return sum;
+}
+
+// Sweep 2.  C_m = (x_{m+1} - x_{m-1}) * w_m for 1 <= m <= Ni-2 (0 on the first and last row);  G_rows(i) = C_{i-1} - C_{i+1}.
+template <typename T, int VEC, bool Z_ON, bool T_ON, int R, bool TS>
+PYTVB_HD void strip_rows_G_central(T* g_plane, const GradPlane<T>& pl, const Params<T>& P, int i0, int j0) {
+    const int Nj = P.Nj, Ni = P.Ni;
+    const int o0 = i0 * Nj + j0;
+    auto row = [&](int m) { return o0 + ((m < 0 ? 0 : (m > Ni - 1 ? Ni - 1 : m)) - i0) * Nj; };   // offset of row m, clamped
+    auto valid = [&](int m) { return m >= 1 && m <= Ni - 2; };
+    T xc[VEC], xp[VEC], Cm[VEC], Cc[VEC];     // rows i and i+1 of x; C_{i-1}, C_i
+    ld_into<T, VEC>(xc, pl.x + o0);
+    ld_into<T, VEC>(xp, pl.x + row(i0 + 1));
+    {
+        T xm2[VEC], xm1[VEC], wm1[VEC], w0[VEC];
+        ld_into<T, VEC>(xm2, pl.x + row(i0 - 2));
+        ld_into<T, VEC>(xm1, pl.x + row(i0 - 1));
+        ld_into<T, VEC>(wm1, pl.w + row(i0 - 1));
+        ld_into<T, VEC>(w0, pl.w + o0);
+        const T vm = valid(i0 - 1) ? T(1) : T(0), vc = valid(i0) ? T(1) : T(0);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            Cm[e] = vm * ((xc[e] - xm2[e]) * wm1[e]);
+            Cc[e] = vc * ((xp[e] - xm1[e]) * w0[e]);
+        }
+    }
+    int o = o0;
+    constexpr int UNR = PYTVB_TVGRAD_UNROLL;
+#pragma unroll(UNR)
+    for (int r = 0; r < R; ++r) {
+        const int i = i0 + r;
+        if (r == 0 || i < Ni) {
+            T x2[VEC], wn[VEC], g[VEC];
+            ld_into<T, VEC>(x2, pl.x + row(i + 2));
+            ld_into<T, VEC>(wn, pl.w + row(i + 1));
+            const T vn = valid(i + 1) ? T(1) : T(0);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const T Cn = vn * ((x2[e] - xc[e]) * wn[e]);
+                g[e] = Cm[e] - Cn;
+                Cm[e] = Cc[e];
+                Cc[e] = Cn;
+                xc[e] = xp[e];
+                xp[e] = x2[e];
+            }
+            strip_quad_G_impl<T, VEC, CENTRAL, Z_ON, T_ON, TS && T_ON, false>(g_plane, pl, P, i, j0, o, g);
+            o += Nj;
+        }
+    }
 }
 
 }  // namespace pytvb

@@ -184,17 +184,29 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct ETV2 {
         T* Wz0 = const_cast<T*>(a.W.base);
         double tv = 0;
         if constexpr (SCHEME == CENTRAL) {
-            for_each_quad_strip(a.z_lo, a.nz, a.P.M, a.P.Ni, a.P.Nj, VEC, [&](int z, int t, int i, int j0, int o, int o_up, int o_dn) {
-                const DualPlane<T> pl = make_dual_plane<T, SCHEME>(a.X, Wz0, a.P, z, t);
-                const long long img = (long long)z * a.P.sZ + (long long)t * a.P.sT;
-                const bool own = z >= 0 && z < a.P.Nz;
-                const T v = (a.P.tscale ? strip_quad_tv_norm<T, VEC, SCHEME, Z, TT, true>(Wz0 + img, (a.out2 && own) ? a.out2 + img : nullptr, pl, a.P, i, j0, o, o_up, o_dn) : strip_quad_tv_norm<T, VEC, SCHEME, Z, TT, false>(Wz0 + img, (a.out2 && own) ? a.out2 + img : nullptr, pl, a.P, i, j0, o, o_up, o_dn));
-                if (own) tv += (double)v;
-            });
-            for_each_quad_strip(0, a.P.Nz, a.P.M, a.P.Ni, a.P.Nj, VEC, [&](int z, int t, int i, int j0, int o, int, int) {
-                const GradPlane<T> pl = make_grad_plane<T, SCHEME>(a.X, a.W, a.P, z, t);
-                if (a.P.tscale) strip_quad_G<T, VEC, SCHEME, Z, TT, true>(a.out + (long long)z * a.P.sZ + (long long)t * a.P.sT, pl, a.P, i, j0, o); else strip_quad_G<T, VEC, SCHEME, Z, TT, false>(a.out + (long long)z * a.P.sZ + (long long)t * a.P.sT, pl, a.P, i, j0, o);
-            });
+            for (int z = a.z_lo; z < a.z_lo + a.nz; ++z)
+                for (int t = 0; t < a.P.M; ++t) {
+                    const DualPlane<T> pl = make_dual_plane<T, SCHEME>(a.X, Wz0, a.P, z, t);
+                    const long long img = (long long)z * a.P.sZ + (long long)t * a.P.sT;
+                    const bool own = z >= 0 && z < a.P.Nz;
+                    T* np = (a.out2 && own) ? a.out2 + img : nullptr;
+                    for (int i0 = 0; i0 < a.P.Ni; i0 += EMUL_R)
+                        for (int j0 = 0; j0 < a.P.Nj; j0 += VEC) {
+                            const T v = a.P.tscale ? strip_rows_tv_norm_central<T, VEC, Z, TT, EMUL_R, TT, TT>(Wz0 + img, np, pl, a.P, i0, j0)
+                                                   : strip_rows_tv_norm_central<T, VEC, Z, TT, EMUL_R, false, TT>(Wz0 + img, np, pl, a.P, i0, j0);
+                            if (own) tv += (double)v;
+                        }
+                }
+            for (int z = 0; z < a.P.Nz; ++z)
+                for (int t = 0; t < a.P.M; ++t) {
+                    const GradPlane<T> pl = make_grad_plane<T, SCHEME>(a.X, a.W, a.P, z, t);
+                    T* gp = a.out + (long long)z * a.P.sZ + (long long)t * a.P.sT;
+                    for (int i0 = 0; i0 < a.P.Ni; i0 += EMUL_R)
+                        for (int j0 = 0; j0 < a.P.Nj; j0 += VEC) {
+                            if (a.P.tscale) strip_rows_G_central<T, VEC, Z, TT, EMUL_R, true>(gp, pl, a.P, i0, j0);
+                            else strip_rows_G_central<T, VEC, Z, TT, EMUL_R, false>(gp, pl, a.P, i0, j0);
+                        }
+                }
         } else {
             for (int z = a.z_lo; z < a.z_lo + a.nz; ++z)
                 for (int t = 0; t < a.P.M; ++t) {
