@@ -658,7 +658,7 @@ PYTVB_HD void strip_quad_G(T* g_plane, const GradPlane<T>& pl, const Params<T>& 
 }
 
 // ------------------------------------------------------------------------------------------------
-// TV sweeps, row-marching form (one-sided and hybrid schemes; the centred scheme keeps the per-row form above).
+// TV sweeps, row-marching form (one-sided and hybrid schemes here; the centred scheme marches its rows further below).
 // A thread walks down the R rows of its strip and keeps the current row, and the row difference (sweep 1) or row term
 // (sweep 2) it shares with the next row, in registers: one new row load per array and row instead of three, every
 // difference / product that two neighbouring voxels share is computed once, and the axis weights are applied to sums of
