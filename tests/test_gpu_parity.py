@@ -306,6 +306,26 @@ def test_non_square_and_unaligned_paths():
         np.testing.assert_allclose(G_u, G_a, atol=1e-6)
 
 
+@pytest.mark.parametrize("masked", [False, True], ids=["nomask", "mask_static"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64], ids=["f32", "f64"])
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_tv_wide_rows_match_oracle(scheme, dtype, masked):
+    """Rows wide enough that every warp of the TV sweeps covers 32 consecutive quads of one row (the lane exchange of
+    sweep 2), 44 rows = five full strips of 8 and one that overhangs the image, both kernel variants of the time factor."""
+    rs = np.random.RandomState(23)
+    shape = (3, 3, 44, 1024)
+    x = rs.rand(*shape).astype(dtype)
+    kw = dict(reg_z_over_reg=0.7, reg_time=0.3)
+    if masked:
+        kw.update(mask_static=rs.rand(1, 1, shape[2], shape[3]) > 0.5, factor_reg_static=2.0)
+    tv, G, n = tv_(scheme)(x.copy(), return_grad_norms=True, **kw)
+    tv_o, G_o, n_o = orc.tv(x.astype(np.float64), scheme, return_grad_norms=True, **kw)
+    f64 = dtype == np.float64
+    assert float(tv) == pytest.approx(tv_o, rel=1e-13 if f64 else 1e-5)       # north-star tolerances for float32
+    np.testing.assert_allclose(G, G_o, atol=1e-10 if f64 else 1e-5)
+    np.testing.assert_allclose(n, n_o, atol=1e-13 if f64 else 1e-5)
+
+
 @pytest.mark.parametrize("shape", [(3, 2, 101, 101), (2, 3, 37, 1001), (5, 1, 300, 130), (2, 2, 130, 258)], ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("scheme", SCHEMES)
 def test_odd_and_multi_block_shapes(scheme, shape):
