@@ -177,10 +177,12 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct EDT2 {
     }
 };
 // TV sweeps as the strip kernels run them: the centred scheme row by row, the other schemes in row-marching strips of
-// EMUL_R rows per thread (strip_rows_tv_norm / strip_rows_G), incl. a last strip that overhangs the image.
-constexpr int EMUL_R = 4;
+// EMUL_R rows per thread (strip_rows_tv_norm / strip_rows_G), incl. a last strip that overhangs the image.  The library
+// runs R = 8 (tv.cu: PYTVB_STRIP_R); pytvb_emulate_set_rows switches the emulation between 4 and 8.
+static int g_emul_rows = 8;
 template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct ETV2 {
-    static int run(const EArgs<T>& a) {
+    static int run(const EArgs<T>& a) { return g_emul_rows == 4 ? run_r<4>(a) : run_r<8>(a); }
+    template <int EMUL_R> static int run_r(const EArgs<T>& a) {
         T* Wz0 = const_cast<T*>(a.W.base);
         double tv = 0;
         if constexpr (SCHEME == CENTRAL) {
@@ -497,4 +499,5 @@ extern "C" int pytvb_emulate_fused(const pytvb_problem* pb, int variant, const v
     return pb->dtype == PYTVB_F32 ? run_fused_emul<float>(pb, variant, u, y, x, aux, x0, lam, sigma, tau, c2, lag, force_scalar, ilo, ihi, flo, fhi, sums)
                                   : run_fused_emul<double>(pb, variant, u, y, x, aux, x0, lam, sigma, tau, c2, lag, force_scalar, ilo, ihi, flo, fhi, sums);
 }
+extern "C" void pytvb_emulate_set_rows(int r) { g_emul_rows = (r == 4) ? 4 : 8; }
 extern "C" const char* pytvb_emulate_error(void) { return g_err; }

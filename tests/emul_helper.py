@@ -41,6 +41,11 @@ def emul():
     return _h
 
 
+def set_tv_rows(r):
+    """Rows per thread of the emulated TV sweeps: 8 (what libpytv_b200.so runs) or 4."""
+    emul().pytvb_emulate_set_rows(int(r))
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 

@@ -11,13 +11,16 @@ from oracle import tv_oracle as orc
 SCHEMES = cases.SCHEMES
 
 
-@pytest.fixture(params=[1, 2], ids=["gen1", "gen2"])
+@pytest.fixture(params=[(1, 8), (2, 8), (2, 4)], ids=["gen1", "gen2", "gen2-r4"])
 def gen(request):
-    """Both kernel generations (tv_core.cuh quad code, strip_core.cuh strip code)."""
+    """Both kernel generations (tv_core.cuh quad code, strip_core.cuh strip code); the strip code's TV sweeps with 8 rows per
+    thread (what the library runs) and with 4 (other strip / image-height alignments)."""
     old = em.GEN
-    em.GEN = request.param
-    yield request.param
+    em.GEN, rows = request.param
+    em.set_tv_rows(rows)
+    yield em.GEN
     em.GEN = old
+    em.set_tv_rows(8)
 
 
 def _tol(dtype):
@@ -335,6 +338,21 @@ def test_central_nz2_intent(gen):
         tvo, Go = orc.tv(x.copy(), "central", **kw)
         assert tv == pytest.approx(tvo, rel=1e-13)
         np.testing.assert_allclose(G, Go, atol=1e-12)
+
+
+@pytest.mark.parametrize("Ni", [1, 2, 3, 7, 8, 9, 15, 17])
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_tv_image_heights_around_the_strip_height(scheme, Ni, gen):
+    """The row-marching TV sweeps with images shorter than, equal to and just past a multiple of the strip height."""
+    rs = np.random.RandomState(31 + Ni)
+    x = rs.rand(3, 2, Ni, 8)
+    ms = rs.rand(1, 1, Ni, 8) > 0.5
+    for kw in (dict(reg_time=0.5), dict(reg_z_over_reg=0.3, reg_time=0.7, mask_static=ms, factor_reg_static=3.0)):
+        tv, G, n = em.tv(x, scheme, **kw)
+        tvo, Go, no = orc.tv(x.copy(), scheme, return_grad_norms=True, **kw)
+        assert tv == pytest.approx(tvo, rel=1e-13)
+        np.testing.assert_allclose(G, Go, atol=1e-12)
+        np.testing.assert_allclose(n, no, atol=1e-13)
 
 
 def test_non_square_images(gen):
