@@ -118,12 +118,17 @@ def cp_primal(y, x, aux, x0, scheme, tau, c2, variant, lo=None, hi=None, z_offse
     return _call(4 if GEN == 1 else 6, pb, np.ascontiguousarray(y), x, aux=aux, x0=x0, lo=lo, hi=hi, c0=tau, c1=c2, variant=variant, scalar=scalar)
 
 
-def _call_mirror(op, pb, inp, out, aux, x0, lo, hi, mp, mn, c0, c1, variant, scalar):
+def _mirror_protos():
     h = emul()
     VP = ctypes.c_void_p
     h.pytvb_emulate_mirror.restype = ctypes.c_int
     h.pytvb_emulate_mirror.argtypes = [ctypes.c_int, ctypes.POINTER(_lib.Problem)] + [VP] * 8 + [ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                                                                               ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    return h
+
+
+def _call_mirror(op, pb, inp, out, aux, x0, lo, hi, mp, mn, c0, c1, variant, scalar):
+    h = _mirror_protos()
     s = ctypes.c_double(0.0)
     rc = h.pytvb_emulate_mirror(op, ctypes.byref(pb), _ptr(inp), _ptr(out), _ptr(aux), _ptr(x0), _ptr(lo), _ptr(hi), _ptr(mp), _ptr(mn), c0, c1,
                                 variant, int(scalar), ctypes.byref(s))
@@ -206,6 +211,25 @@ class EmulOps:
     def workspace(self, pb, device):
         import torch
         return torch.empty(1, dtype=torch.uint8)
+
+    # the passes with mirror stores (peer-memory halo push); mirror_prev / mirror_next are raw addresses or None
+    def cp_dual_p2p(self, pb, xbar, y, lam, sigma, d_l21, lo, hi, mirror_prev, mirror_next, ws):
+        s = ctypes.c_double(0.0)
+        _mirror_protos()
+        rc = emul().pytvb_emulate_mirror(0, ctypes.byref(pb), self._p(xbar), self._p(y), None, None, self._p(lo), self._p(hi), mirror_prev, mirror_next,
+                                         sigma, 1.0 / lam, 0, 0, ctypes.byref(s))
+        assert rc == 0
+        if d_l21 is not None:
+            d_l21[0] = s.value
+
+    def cp_primal_p2p(self, variant, pb, y, x, aux, x0, tau, c2, d_fid, lo, hi, mirror_prev, mirror_next, ws):
+        s = ctypes.c_double(0.0)
+        _mirror_protos()
+        rc = emul().pytvb_emulate_mirror(1, ctypes.byref(pb), self._p(y), self._p(x), self._p(aux), self._p(x0), self._p(lo), self._p(hi), mirror_prev,
+                                         mirror_next, tau, c2, 0 if variant == "rof" else 1, 0, ctypes.byref(s))
+        assert rc == 0
+        if d_fid is not None:
+            d_fid[0] = s.value
 
 
 class EmulSlabOps:

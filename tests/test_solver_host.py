@@ -40,3 +40,25 @@ def test_partition_z_covers_the_volume():
             assert parts[0][0] == 0 and sum(c for _, c in parts) == Nz
             assert all(parts[k][0] + parts[k][1] == parts[k + 1][0] for k in range(world - 1))
             assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+
+
+@pytest.mark.parametrize("variant", ["rof", "readme"])
+@pytest.mark.parametrize("scheme", ["upwind", "downwind", "central", "hybrid"])
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_push_schedule_through_the_executor_interface(scheme, variant, dtype):
+    """tests/p2p_schedule.py (the harness the single-GPU test of the `_p2p` entry points uses) with the host-emulated
+    executor: slabs pushing their boundary planes into each other's halo planes equal the whole volume bit for bit."""
+    import torch
+    import p2p_schedule
+    slabs, whole = p2p_schedule.run(em.EmulOps(), torch.device("cpu"), scheme, variant, getattr(torch, dtype))
+    for a, b in zip(slabs, whole):
+        assert torch.equal(a, b)
+
+
+def test_push_schedule_uneven_slabs_wide_planes():
+    import torch
+    import p2p_schedule
+    slabs, whole = p2p_schedule.run(em.EmulOps(), torch.device("cpu"), "hybrid", "rof", torch.float32, shape=(7, 3, 70, 520),
+                                    bounds=((0, 2), (2, 3), (3, 7)), iterations=2)
+    for a, b in zip(slabs, whole):
+        assert torch.equal(a, b)
