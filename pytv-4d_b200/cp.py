@@ -295,9 +295,10 @@ class CPSolver:
             interior_lo, interior_hi = self.halo.prev is not None, self.halo.next is not None
             need_img_lo, need_img_hi = scheme != "upwind", scheme != "downwind"
             need_fld_lo, need_fld_hi = scheme != "downwind", scheme != "upwind"
-            p2p_ok = ops is None and self._ts is None and self.dual_dtype == dt and not self.overlap
+            p2p_ok = (ops is None and self._ts is None and self.dual_dtype == dt and not self.overlap
+                      and str(self.halo.dist.get_backend(self.halo.group)).lower() == "nccl")
             if comm == "p2p" and not p2p_ok:
-                raise ValueError("comm='p2p' needs the CUDA executor, the blocking schedule, no time_weight and full-precision duals")
+                raise ValueError("comm='p2p' needs the CUDA executor over an NCCL group, the blocking schedule, no time_weight and full-precision duals")
             if comm != "nccl" and p2p_ok:
                 # measured on 8 x B200 (profiles/r01zb_*): 9.86 ms per iteration against 10.18 ms with send/recv (one GPU: 9.60)
                 try:
