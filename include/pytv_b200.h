@@ -53,8 +53,7 @@ typedef struct pytvb_problem {
     double factor_reg_static;   /* time weight multiplier where mask_static is set */
     const uint8_t* mask_static; /* device (Ni, Nj) bytes, nonzero = static pixel; NULL = none */
     const void* time_scale;     /* EXTENSION (reference TODO, README.md:258): device (Nz, M, Ni, Nj) array of `dtype`, the per-voxel factor
-                                 * of the time component(s) = sqrt of a weight map; multiplies on top of mask_static; NULL = none.
-                                 * Not available for slabs with z halos in pytvb_tv, nor with PYTVB_GEN=1. */
+                                 * of the time component(s) = sqrt of a weight map; multiplies on top of mask_static; NULL = none. */
 } pytvb_problem;
 
 int pytvb_version(void);
@@ -136,18 +135,6 @@ int pytvb_cp_dual_f16y(const pytvb_problem* pb, const void* xbar, void* y_half, 
                        const void* halo_lo, const void* halo_hi, void* ws, void* stream);
 int pytvb_cp_primal_rof_f16y(const pytvb_problem* pb, const void* y_half, void* x, void* xbar, const void* x0, double lam, double tau,
                              double theta, double* d_fid_or_null, const void* halo_lo_half, const void* halo_hi_half, void* ws, void* stream);
-
-/* Both passes of one iteration in ONE launch: pass-B tiles follow pass-A tiles a few z-planes behind (ordered by
- * tickets, synchronised by per-plane completion counters), so that pass B reads y from L2 instead of DRAM
- * (4(3Nd+5) -> 4(2Nd+5) bytes per voxel).  Same arithmetic and results as pytvb_cp_dual + pytvb_cp_primal_*.
- * u = the image the dual pass differentiates (xbar for variant 0 / rof: pass aux; x for variant 1 / readme);
- * aux = xbar (rof, out) or y_f (readme, in/out); c2 = theta (rof) or sigma_A (readme).
- * Image halos as pytvb_D, field halos as pytvb_DT.  ws: pytvb_fused_workspace_bytes().  If a wait inside the
- * kernel times out (it never should), the two energy outputs are set to NaN. */
-size_t pytvb_fused_workspace_bytes(const pytvb_problem* pb);
-int pytvb_cp_iter_fused(const pytvb_problem* pb, int variant, const void* u, void* y, void* x, void* aux, const void* x0, double lam,
-                        double sigma, double tau, double c2, double* d_l21_or_null, double* d_fid_or_null, const void* img_halo_lo,
-                        const void* img_halo_hi, const void* fld_halo_lo, const void* fld_halo_hi, void* ws, void* stream);
 
 /* ---- host-buffer entry points: what a caller without device memory management binds -------------------
  * tv_<scheme> with numpy-style HOST arrays in and out (the reference's default call: numpy in, numpy out,

@@ -65,9 +65,6 @@ _PROTOTYPES = {
     "pytvb_cp_primal_p2p": (ctypes.c_int, [_PB, ctypes.c_int, _VP, _VP, _VP, _VP, ctypes.c_double, ctypes.c_double, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "pytvb_cp_dual_f16y": (ctypes.c_int, [_PB, _VP, _VP, ctypes.c_double, ctypes.c_double, _VP, _VP, _VP, _VP, _VP]),
     "pytvb_cp_primal_rof_f16y": (ctypes.c_int, [_PB, _VP, _VP, _VP, _VP, ctypes.c_double, ctypes.c_double, ctypes.c_double, _VP, _VP, _VP, _VP, _VP]),
-    "pytvb_fused_workspace_bytes": (ctypes.c_size_t, [_PB]),
-    "pytvb_cp_iter_fused": (ctypes.c_int, [_PB, ctypes.c_int, _VP, _VP, _VP, _VP, _VP, ctypes.c_double, ctypes.c_double, ctypes.c_double,
-                                            ctypes.c_double, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "pytvb_tv_host": (ctypes.c_int, [_PB, _VP, _VP, _VP, ctypes.POINTER(ctypes.c_double)]),
     "pytvb_cp_create": (ctypes.c_int, [_PB, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.POINTER(_VP)]),
     "pytvb_cp_reset_host": (ctypes.c_int, [_VP, _VP]),

@@ -38,13 +38,14 @@ def partition_z(Nz_global, world_size):
     return out
 
 
-def operator_norm_sq_bound(scheme, z_on, t_on, reg_z_over_reg, reg_time, factor_reg_static, has_mask_static):
-    """Upper bound of |D|^2: 4 per unit-weight axis for the one-sided schemes and hybrid, 1 for central."""
+def operator_norm_sq_bound(scheme, z_on, t_on, reg_z_over_reg, reg_time, factor_reg_static, has_mask_static, max_time_weight=1.0):
+    """Upper bound of |D|^2: 4 per unit-weight axis for the one-sided schemes and hybrid, 1 for central.  The time axis
+    carries reg_time x (factor_reg_static where mask_static) x (the largest entry of a time_weight map)."""
     w = 2.0
     if z_on:
         w += reg_z_over_reg
     if t_on:
-        w += reg_time * (max(1.0, factor_reg_static) if has_mask_static else 1.0)
+        w += reg_time * (max(1.0, factor_reg_static) if has_mask_static else 1.0) * max(1.0, float(max_time_weight))
     return w if scheme == "central" else 4.0 * w
 
 
@@ -89,23 +90,16 @@ class CudaOps:
     def adjoint(self, pb, y, out, lo, hi):
         _lib.check(self.lib.pytvb_DT(ctypes.byref(pb), _dev.ptr(y), _dev.ptr(out), _dev.ptr(lo), _dev.ptr(hi), _dev.stream_ptr()))
 
-    def fused_workspace(self, pb, device):
-        return torch.empty(self.lib.pytvb_fused_workspace_bytes(ctypes.byref(pb)), dtype=torch.uint8, device=device)
-
-    def cp_iter_fused(self, variant, pb, u, y, x, aux, x0, lam, sigma, tau, c2, d_l21, d_fid, ws):
-        _lib.check(self.lib.pytvb_cp_iter_fused(ctypes.byref(pb), 0 if variant == "rof" else 1, _dev.ptr(u), _dev.ptr(y), _dev.ptr(x), _dev.ptr(aux),
-                                                _dev.ptr(x0), lam, sigma, tau, c2, _dev.ptr(d_l21), _dev.ptr(d_fid), None, None, None, None,
-                                                _dev.ptr(ws), _dev.stream_ptr()))
-
 
 class HaloExchange:
     """Nearest-neighbour plane exchange between z-slabs over torch.distributed (NCCL send/recv on NVLink;
     gloo in the CPU tests)."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, reduce_group=None):
         import torch.distributed as dist
         self.dist = dist
         self.group = group
+        self._reduce_group = reduce_group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.prev = self.rank - 1 if self.rank > 0 else None
@@ -147,12 +141,18 @@ class HaloExchange:
         return t
 
     def allreduce_sum_async(self, t):
-        """Scalar all-reduce on a communicator of its own, so that it never queues in front of the halo send/recv of
-        the next pass (one NCCL communicator executes its operations in order).  Returns the work handle."""
-        if getattr(self, "_reduce_group", None) is None:
-            ranks = list(range(self.dist.get_world_size())) if self.group is None else self.dist.get_process_group_ranks(self.group)
-            self._reduce_group = self.dist.new_group(ranks=ranks)      # collective: every rank of the solver gets here
-        return self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self._reduce_group, async_op=True)
+        """Scalar all-reduce, asynchronously; returns the work handle.  With a communicator of its own (`reduce_group`,
+        see make_reduce_group) it never queues in front of the halo send/recv of the next pass (one NCCL communicator
+        executes its operations in order); without one it runs on the solver's group."""
+        g = self._reduce_group if self._reduce_group is not None else self.group
+        return self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=g, async_op=True)
+
+    def make_reduce_group(self):
+        """Create the second communicator for the scalar all-reduces.  `new_group` is collective over the DEFAULT process
+        group, so this is only done when the solver spans the default group (every rank then gets here, in the solver's
+        constructor); a solver on a sub-group takes a caller-made `reduce_group` or shares its group."""
+        if self._reduce_group is None and self.group is None:
+            self._reduce_group = self.dist.new_group(ranks=list(range(self.dist.get_world_size())))
 
 
 class PeerHalos:
@@ -197,7 +197,7 @@ class CPSolver:
 
     def __init__(self, x0, lam, scheme="hybrid", variant="rof", sigma=0.5, tau=None, theta=1.0, sigma_A=1.0, reg_z_over_reg=1.0,
                  reg_time=0.0, mask_static=False, factor_reg_static=0, distributed=False, group=None, z_offset=None, Nz_global=None,
-                 ops=None, track_energy=True, fused=None, dual_dtype=None, time_weight=None, comm=None):
+                 ops=None, track_energy=True, dual_dtype=None, time_weight=None, comm=None, reduce_group=None):
         if scheme not in _dev.SCHEMES:
             raise ValueError("unknown scheme %r" % (scheme,))
         if variant not in ("rof", "readme"):
@@ -214,8 +214,12 @@ class CPSolver:
         else:   # injected executor (CPU tests): keep the array where it is
             self.x0 = torch.as_tensor(np.ascontiguousarray(x0)).clone() if not isinstance(x0, torch.Tensor) else x0.clone().contiguous()
         dev, dt = self.x0.device, self.x0.dtype
-        self.halo = HaloExchange(group) if (distributed or group is not None) else None
+        self.halo = HaloExchange(group, reduce_group) if (distributed or group is not None) else None
         if self.halo is not None and self.halo.world > 1:
+            if track_energy:
+                self.halo.make_reduce_group()
+            if (Nz_global is None) != (z_offset is None):
+                raise ValueError("sharded solver: give both z_offset and Nz_global, or neither (they are then derived from the ranks' plane counts)")
             if Nz_global is None:
                 counts = torch.zeros(self.halo.world, dtype=torch.int64, device=dev)
                 counts[self.halo.rank] = shape[0]
@@ -236,9 +240,18 @@ class CPSolver:
                 self._ms = (m.reshape(shape[2], shape[3]) != 0).to(torch.uint8).contiguous()
         # extension (reference TODO, README.md:258): per-voxel weight map of the time regularisation for this slab
         self._ts = None
+        max_tw = 1.0
         if time_weight is not None:
             w = time_weight if isinstance(time_weight, torch.Tensor) else torch.as_tensor(np.asarray(time_weight))
-            self._ts = torch.sqrt(torch.broadcast_to(w.to(dev).to(torch.float64), shape)).to(dt).contiguous()
+            w = torch.broadcast_to(w.to(dev).to(torch.float64), shape)
+            if bool((w < 0).any()):
+                raise ValueError("time_weight must be >= 0")
+            self._ts = torch.sqrt(w).to(dt).contiguous()
+            # the default step size needs |D|^2, which grows with the largest weight (of the WHOLE volume when sharded)
+            mx = w.max().reshape(1).clone()
+            if self.halo is not None:
+                self.halo.dist.all_reduce(mx, op=self.halo.dist.ReduceOp.MAX, group=self.halo.group)
+            max_tw = float(mx.item())
         self.pb = _lib.make_problem(scheme, _lib.F32 if dt == torch.float32 else _lib.F64, shape, float(reg_z_over_reg), float(reg_time),
                                     float(factor_reg_static), self._ms.data_ptr() if self._ms is not None else None, self.z_offset,
                                     self.Nz_global, self._ts.data_ptr() if self._ts is not None else None)
@@ -247,7 +260,7 @@ class CPSolver:
         self.Nd = (4 + 2 * self.z_on + 2 * self.t_on) if scheme == "hybrid" else (2 + self.z_on + self.t_on)
         if tau is None:
             L2 = operator_norm_sq_bound(scheme, self.z_on, self.t_on, float(reg_z_over_reg), float(reg_time), float(factor_reg_static),
-                                        self._ms is not None)
+                                        self._ms is not None, max_tw)
             tau = 1.0 / (L2 + 1.0)
         self.tau = float(tau)
         # state
@@ -274,12 +287,6 @@ class CPSolver:
         self._field_req = None     # outstanding exchange of the field halos for the primal pass
         self._pb_cache = {}
         self.ws = self.ops.workspace(self.pb, dev)
-        # single-launch iteration (generation 3): pass B follows pass A a few planes behind inside one kernel and
-        # reads y from L2.  Whole volumes on one GPU only; PYTVB_FUSED=1 or fused=True selects it.
-        if fused is None:
-            fused = os.environ.get("PYTVB_FUSED", "0") == "1"
-        self.fused = bool(fused) and self.halo is None and hasattr(self.ops, "cp_iter_fused") and self.dual_dtype == dt
-        self._fused_ws = self.ops.fused_workspace(self.pb, dev) if self.fused else None
         self.iterations = 0
         # halo planes.  comm="p2p": no exchange step at all - the planes live in symmetric memory and the passes of the
         # neighbouring ranks store into them (PeerHalos); comm="nccl": send/recv between the passes; "auto" (default,
@@ -477,24 +484,27 @@ class CPSolver:
         self.x.copy_(state[0]); self.aux.copy_(state[1]); self.y.copy_(state[2]); self.scal.copy_(state[3])
         self.iterations = state[4]
         self._graph, self._graph_iters = g, int(iterations)
+        self._graph_key = self._graph_state_key()
         return self
+
+    def _graph_state_key(self):
+        """What a captured graph has baked in: buffer addresses and the scalar parameters of the passes."""
+        return (self.x0.data_ptr(), self.x.data_ptr(), self.aux.data_ptr(), self.y.data_ptr(), self.lam, self.sigma, self.tau, self.theta, self.sigma_A)
 
     def step(self, n=1):
         """Run n iterations; returns self."""
         g = getattr(self, "_graph", None)
+        if g is not None and self._graph_key != self._graph_state_key():
+            # x0 was rebound (step_host_async) or lam / tau / sigma changed (TVProx): the recorded launches are stale
+            g = self._graph = None
         if g is not None and not torch.cuda.is_current_stream_capturing():
             while n >= self._graph_iters:
                 g.replay()
                 self.iterations += self._graph_iters
                 n -= self._graph_iters
         for _ in range(n):
-            if self.fused:
-                c2 = self.theta if self.variant == "rof" else self.sigma_A
-                self.ops.cp_iter_fused(self.variant, self.pb, self._dual_input(), self.y, self.x, self.aux, self.x0, self.lam, self.sigma, self.tau, c2,
-                                       self.scal[0:1] if self.track_energy else None, self.scal[3:4] if self.track_energy else None, self._fused_ws)
-            else:
-                self._pass_A()
-                self._pass_B()
+            self._pass_A()
+            self._pass_B()
             self.iterations += 1
         return self
 
@@ -511,16 +521,19 @@ class CPSolver:
         return self.energy()
 
     # ---- pipelined host streaming: PCIe in both directions overlaps the two passes ------------------------
+    PIPE_DEPTH = 3      # tickets that may be outstanding: upload of step k+1 | passes of step k | download of step k-1
+
     def _pipe_init(self):
         if getattr(self, "_pipe", None) is None:
             dev = self.x0.device
+            D = self.PIPE_DEPTH
             self._pipe = dict(
                 h2d=torch.cuda.Stream(device=dev), d2h=torch.cuda.Stream(device=dev),
-                x0=[self.x0, torch.empty_like(self.x0)],           # double-buffered data term
-                snap=[torch.empty_like(self.x), torch.empty_like(self.x)],   # x snapshots being downloaded
-                scal=[torch.zeros(6, dtype=torch.float64, device=dev) for _ in range(2)],
-                scal_host=[torch.zeros(6, dtype=torch.float64).pin_memory() for _ in range(2)],
-                d2h_done=[None, None], comp_done=[None, None], k=0)
+                x0=[self.x0] + [torch.empty_like(self.x0) for _ in range(D - 1)],   # data term, one buffer per ticket in flight
+                snap=[torch.empty_like(self.x) for _ in range(D)],                  # x snapshots being downloaded
+                scal=[torch.zeros(6, dtype=torch.float64, device=dev) for _ in range(D)],
+                scal_host=[torch.zeros(6, dtype=torch.float64).pin_memory() for _ in range(D)],
+                d2h_done=[None] * D, comp_done=[None] * D, k=0)
         return self._pipe
 
     def step_host_async(self, x0_host, x_out_host=None):
@@ -528,16 +541,22 @@ class CPSolver:
         (second copy stream) and return a ticket at once; `wait(ticket)` returns the energy of that step once its
         download has finished.  Successive calls overlap: while step k computes, the data of step k+1 is being
         uploaded and the image of step k-1 downloaded (PCIe is full duplex), so the steady-state cost per step is
-        max(upload, download, compute) instead of their sum.  At most two tickets may be outstanding (wait for
-        ticket k-1 before issuing step k+1); host buffers must stay untouched until their ticket has been waited for."""
+        max(upload, download, compute) instead of their sum.  At most PIPE_DEPTH (3) tickets may be outstanding (wait
+        for ticket k-2 before issuing step k+1: with only two in flight the link idles while the passes run); host
+        buffers must stay untouched until their ticket has been waited for."""
         p = self._pipe_init()
         k = p["k"]
-        slot = k % 2
+        slot = k % self.PIPE_DEPTH
         cur = torch.cuda.current_stream()
         src = x0_host if isinstance(x0_host, torch.Tensor) else torch.from_numpy(x0_host)
-        # upload into the data buffer last read by step k-2 (step k-1 is reading the other one)
+        # upload into the data buffer last read by step k-DEPTH; a buffer used for the first time may still be read (or be
+        # initialised) by work enqueued on the current stream, e.g. the constructor's copies or earlier step() calls
         if p["comp_done"][slot] is not None:
             p["h2d"].wait_event(p["comp_done"][slot])
+        else:
+            first = torch.cuda.Event()
+            first.record(cur)
+            p["h2d"].wait_event(first)
         with torch.cuda.stream(p["h2d"]):
             p["x0"][slot].copy_(src, non_blocking=True)
             up = torch.cuda.Event()
@@ -546,7 +565,7 @@ class CPSolver:
         self.x0 = p["x0"][slot]
         self.step(1)
         if p["d2h_done"][slot] is not None:
-            cur.wait_event(p["d2h_done"][slot])        # snapshot slot: the download of step k-2 has finished
+            cur.wait_event(p["d2h_done"][slot])        # snapshot slot: the download of step k-DEPTH has finished
         p["snap"][slot].copy_(self.x)
         p["scal"][slot].copy_(self.scal)
         done = torch.cuda.Event()

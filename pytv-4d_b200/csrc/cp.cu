@@ -3,7 +3,6 @@
 
 #include "host_common.cuh"
 #include "kernels2.cuh"
-#include "kernels3.cuh"
 
 #ifndef PYTVB_STRIP_R
 #define PYTVB_STRIP_R 4   // image rows walked by one thread in the generation-2 kernels
@@ -13,18 +12,11 @@ using namespace pytvb;
 
 namespace {
 
-// Generation 2 (strip kernels) is the default for the vector and the scalar path alike; generation 1 (one
-// quad per thread, exact IEEE division / sqrt) is kept as a cross-check and is selected with PYTVB_GEN=1.
-bool use_gen2() {
-    const char* e = getenv("PYTVB_GEN");
-    return !e || atoi(e) >= 2;
-}
-
 template <typename T> struct DualArgs { ImgView<T> Xb; T* y; double* partial; Params<T> P; T sigma, inv_lam, lam; cudaStream_t st; long long* nb; T* mir_prev; T* mir_next; };
 template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchDual {
     static int run(const DualArgs<T>& a) {
         {
-            if (use_gen2()) {
+            {
                 constexpr int R = PYTVB_STRIP_R;
                 const Tiling tl = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.P.Nz, VEC);
                 if (int rc = check_grid(tl)) return rc;
@@ -42,13 +34,6 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchDual {
                 return PYTVB_OK;
             }
         }
-        const Tiling tl = make_tiling(a.P.Nj, a.P.Ni, a.P.M, 0, a.P.Nz, VEC);
-        if (int rc = check_grid(tl)) return rc;
-        cp_dual_kernel<T, VEC, SCHEME, Z, TT><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.Xb, a.y, a.partial, a.P, a.sigma, a.inv_lam, tl);
-        count_launches(1);
-        PYTVB_CUDA(cudaGetLastError());
-        *a.nb = tl.nblocks;
-        return PYTVB_OK;
     }
 };
 
@@ -58,7 +43,7 @@ template <typename T> struct PrimalArgs {
 template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchPrimal {
     static int run(const PrimalArgs<T>& a) {
         {
-            if (use_gen2()) {
+            {
                 constexpr int R = PYTVB_STRIP_R;
                 const Tiling tl = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.P.Nz, VEC);
                 if (int rc = check_grid(tl)) return rc;
@@ -88,16 +73,6 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchPrimal 
                 return PYTVB_OK;
             }
         }
-        const Tiling tl = make_tiling(a.P.Nj, a.P.Ni, a.P.M, 0, a.P.Nz, VEC);
-        if (int rc = check_grid(tl)) return rc;
-        if (a.variant == 0)
-            cp_primal_kernel<T, VEC, SCHEME, Z, TT, 0><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.Y, a.x, a.aux, a.x0, a.partial, a.P, a.tau, a.c2, tl);
-        else
-            cp_primal_kernel<T, VEC, SCHEME, Z, TT, 1><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.Y, a.x, a.aux, a.x0, a.partial, a.P, a.tau, a.c2, tl);
-        count_launches(1);
-        PYTVB_CUDA(cudaGetLastError());
-        *a.nb = tl.nblocks;
-        return PYTVB_OK;
     }
 };
 
@@ -164,7 +139,6 @@ int pytvb_cp_dual_p2p(const pytvb_problem* pb, const void* xbar, void* y, double
     PYTVB_REQUIRE(xbar && y, "xbar and y must not be NULL");
     PYTVB_REQUIRE(!d_l21_or_null || ws, "a reduction workspace is required when d_l21 is requested");
     PYTVB_REQUIRE(lam >= 0, "lam must be >= 0");
-    PYTVB_REQUIRE(use_gen2(), "the peer-memory halo push is implemented by the generation-2 kernels only");
     if (int rc = check_halos(pb, axes_of(pb).z_on, false, halo_lo, halo_hi)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     return pb->dtype == PYTVB_F32 ? run_dual<float>(pb, xbar, y, lam, sigma, d_l21_or_null, halo_lo, halo_hi, ws, st, mirror_prev, mirror_next)
@@ -177,7 +151,6 @@ int pytvb_cp_primal_p2p(const pytvb_problem* pb, int variant, const void* y, voi
     PYTVB_REQUIRE(variant == 0 || variant == 1, "variant must be 0 (rof) or 1 (readme)");
     PYTVB_REQUIRE(y && x && aux && x0, "y, x, x0 and the auxiliary image must not be NULL");
     PYTVB_REQUIRE(!d_fid_or_null || ws, "a reduction workspace is required when d_fid is requested");
-    PYTVB_REQUIRE(use_gen2(), "the peer-memory halo push is implemented by the generation-2 kernels only");
     if (int rc = check_halos(pb, axes_of(pb).z_on, true, halo_lo, halo_hi)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     return pb->dtype == PYTVB_F32 ? run_primal<float>(pb, variant, y, x, aux, x0, tau, c2, d_fid_or_null, halo_lo, halo_hi, ws, st, mirror_prev, mirror_next)

@@ -60,10 +60,6 @@ inline int check_problem(const pytvb_problem* pb) {
     PYTVB_REQUIRE(pb->z_offset >= 0 && pb->z_offset + pb->Nz <= pb->Nz_global, "slab [%lld, %lld) outside 0..%lld",
                   (long long)pb->z_offset, (long long)(pb->z_offset + pb->Nz), (long long)pb->Nz_global);
     PYTVB_REQUIRE(!(pb->factor_reg_static < 0), "factor_reg_static must be >= 0");
-    {
-        const char* g = getenv("PYTVB_GEN");
-        PYTVB_REQUIRE(!(pb->time_scale && g && atoi(g) < 2), "time_scale is implemented by the generation-2 kernels only (unset PYTVB_GEN)");
-    }
     return PYTVB_OK;
 }
 
@@ -143,7 +139,7 @@ inline int check_grid(const Tiling& tl) {
 // Workspace layout for reductions: [partials: max CTAs][stage 2: 256 doubles]
 constexpr int REDUCE_STAGE2 = 256;
 inline long long max_partials(const pytvb_problem* pb) {
-    // worst case: generation-1 scalar path (one thread per voxel), one extra halo plane on each side (tv sweep 1)
+    // worst case: scalar path with one row per thread, one extra halo plane on each side (tv sweep 1)
     const Tiling tl = make_tiling((int)pb->Nj, (int)pb->Ni, (int)pb->M, 0, (int)pb->Nz + 2, 1);
     return tl.nblocks;
 }

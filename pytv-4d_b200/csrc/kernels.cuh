@@ -1,8 +1,9 @@
-// sm_100a kernels of the TV hot path (generation 1: one thread per quad, direct neighbour loads).
+// Launch machinery shared by the sm_100a kernels of the TV hot path: tiling, block-index decode, reductions.
 //
-// Work decomposition shared by every kernel here:
-//   * a thread owns one quad (VEC consecutive voxels of a row, one 128-bit access when VEC*sizeof(T)=16);
-//   * a CTA of 256 threads owns TR rows x TW quads of one (z, t) plane;
+// Work decomposition of the strip kernels (kernels2.cuh):
+//   * a thread owns one quad column (VEC consecutive voxels of a row, one 128-bit access when VEC*sizeof(T)=16) and
+//     walks R consecutive rows of it;
+//   * a CTA of 256 threads owns TR thread-rows x TW quads of one (z, t) plane;
 //   * CTAs are numbered so that, for a band of BAND_ROWS image rows, ALL (z, t) planes are visited before
 //     the next band starts.  The z+-1 / t+-1 neighbour rows of a quad (and, for the adjoint, the
 //     neighbouring planes of the dual field) were therefore touched a few hundred CTAs earlier and are
@@ -11,7 +12,7 @@
 //     to a per-CTA slot and summed by a fixed-order second stage: deterministic, no float atomics.
 #pragma once
 #include <cuda_runtime.h>
-#include "tv_core.cuh"
+#include "core.cuh"
 
 namespace pytvb {
 
@@ -137,65 +138,6 @@ static __global__ void __launch_bounds__(CTA_THREADS) reduce_chunks_kernel(const
     if (threadIdx.x == 0) out[blockIdx.x] = s * scale;
 }
 
-// ------------------------------------------------------------------------------------------------
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON>
-__global__ void __launch_bounds__(CTA_THREADS) D_kernel(ImgView<T> X, T* __restrict__ D, Params<T> P, Tiling tl) {
-    typedef Comp<SCHEME, Z_ON, T_ON> C;
-    const QuadIdx q = decode_quad(tl, P.Ni, VEC);
-    if (!q.active) return;
-    T d[C::ND][VEC];
-    quad_D<T, VEC, SCHEME, Z_ON, T_ON>(d, X, P, q.z, q.t, q.i, q.j0);
-    T* o = D + (long long)q.z * P.sZf + (long long)q.t * P.sT + (long long)q.i * P.Nj + q.j0;
-#pragma unroll
-    for (int k = 0; k < C::ND; ++k) {
-        Pack<T, VEC> pk;
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) pk.v[e] = d[k][e];
-        st_pack<T, VEC>(o + (long long)k * P.sC, pk);
-    }
-}
-
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON>
-__global__ void __launch_bounds__(CTA_THREADS) DT_kernel(FieldView<T> Pf, T* __restrict__ out, Params<T> P, Tiling tl) {
-    const QuadIdx q = decode_quad(tl, P.Ni, VEC);
-    if (!q.active) return;
-    T o[VEC];
-    quad_DT<T, VEC, SCHEME, Z_ON, T_ON>(o, Pf, P, q.z, q.t, q.i, q.j0);
-    Pack<T, VEC> pk;
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) pk.v[e] = o[e];
-    st_pack<T, VEC>(out + (long long)q.z * P.sZ + (long long)q.t * P.sT + (long long)q.i * P.Nj + q.j0, pk);
-}
-
-// L2,1 norm of a field with a runtime number of components (compute_L21_norm, tv_operators_GPU.py:46).
-template <typename T, int VEC>
-__global__ void __launch_bounds__(CTA_THREADS) l21_kernel(const T* __restrict__ D, int Nd, T* __restrict__ norms, double* __restrict__ partial,
-                                                          Params<T> P, Tiling tl) {
-    const QuadIdx q = decode_quad(tl, P.Ni, VEC);
-    T sum = T(0);
-    if (q.active) {
-        const long long off = (long long)q.t * P.sT + (long long)q.i * P.Nj + q.j0;
-        const T* p = D + (long long)q.z * P.sZf + off;
-        T s[VEC];
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) s[e] = T(0);
-        for (int k = 0; k < Nd; ++k) {
-            const Pack<T, VEC> v = ld_pack<T, VEC>(p + (long long)k * P.sC);
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) s[e] += v.v[e] * v.v[e];
-        }
-        Pack<T, VEC> nr;
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-            nr.v[e] = pytvb_sqrt(s[e]);
-            sum += nr.v[e];
-        }
-        if (norms) st_pack<T, VEC>(norms + (long long)q.z * P.sZ + off, nr);
-    }
-    const double bs = block_sum((double)sum);
-    if (threadIdx.x == 0) partial[blockIdx.x] = bs;
-}
-
 // img[~mask] = 0 in place (tv_GPU.py:79-80).  mask: one byte per voxel, either the full (Nz,M,Ni,Nj)
 // volume or a single (Ni,Nj) plane broadcast over z and t.
 template <typename T>
@@ -205,82 +147,6 @@ __global__ void __launch_bounds__(CTA_THREADS) apply_mask_kernel(T* __restrict__
     for (long long k = (long long)blockIdx.x * CTA_THREADS + threadIdx.x; k < V; k += stride) {
         const uint8_t m = mask_is_plane ? mask[k % plane] : mask[k];
         if (!m) x[k] = T(0);
-    }
-}
-
-// TV, sweep 1: inverse gradient norm w (0 where the norm is 0) for every plane the sub-gradient sweep
-// reads (the slab plus one plane each side when halos exist), the TV partial sums and, on request, the
-// norm array with the reference's infs (tv_GPU.py:85-88).
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON>
-__global__ void __launch_bounds__(CTA_THREADS) tv_norm_kernel(ImgView<T> X, T* __restrict__ Wbase /* plane z=0 */, T* __restrict__ norms,
-                                                              double* __restrict__ partial, Params<T> P, Tiling tl) {
-    typedef Comp<SCHEME, Z_ON, T_ON> C;
-    const QuadIdx q = decode_quad(tl, P.Ni, VEC);
-    T sum = T(0);
-    if (q.active) {
-        T d[C::ND][VEC], nr[VEC];
-        quad_D<T, VEC, SCHEME, Z_ON, T_ON>(d, X, P, q.z, q.t, q.i, q.j0);
-        quad_norm<T, VEC, C::ND>(nr, d);
-        const long long off = (long long)q.z * P.sZ + (long long)q.t * P.sT + (long long)q.i * P.Nj + q.j0;
-        Pack<T, VEC> w, no;
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-            w.v[e] = nr[e] > T(0) ? T(1) / nr[e] : T(0);
-            no.v[e] = nr[e] > T(0) ? nr[e] : T(INFINITY);
-        }
-        st_pack<T, VEC>(Wbase + off, w);
-        if (q.z >= 0 && q.z < P.Nz) {
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) sum += nr[e];
-            if (norms) st_pack<T, VEC>(norms + off, no);
-        }
-    }
-    const double bs = block_sum((double)sum);
-    if (threadIdx.x == 0) partial[blockIdx.x] = bs;
-}
-
-// TV, sweep 2: sub-gradient from x and w.
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON>
-__global__ void __launch_bounds__(CTA_THREADS) tv_grad_kernel(ImgView<T> X, ImgView<T> W, T* __restrict__ G, Params<T> P, Tiling tl) {
-    const QuadIdx q = decode_quad(tl, P.Ni, VEC);
-    if (!q.active) return;
-    T g[VEC];
-    quad_G<T, VEC, SCHEME, Z_ON, T_ON>(g, X, W, P, q.z, q.t, q.i, q.j0);
-    Pack<T, VEC> pk;
-#pragma unroll
-    for (int e = 0; e < VEC; ++e) pk.v[e] = g[e];
-    st_pack<T, VEC>(G + (long long)q.z * P.sZ + (long long)q.t * P.sT + (long long)q.i * P.Nj + q.j0, pk);
-}
-
-// Chambolle-Pock dual pass (pass A of the iteration).
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON>
-__global__ void __launch_bounds__(CTA_THREADS) cp_dual_kernel(ImgView<T> Xb, T* __restrict__ y, double* __restrict__ partial, Params<T> P, T sigma,
-                                                              T inv_lam, Tiling tl) {
-    const QuadIdx q = decode_quad(tl, P.Ni, VEC);
-    T l21 = T(0);
-    if (q.active) l21 = quad_cp_dual<T, VEC, SCHEME, Z_ON, T_ON>(y, Xb, P, sigma, inv_lam, q.z, q.t, q.i, q.j0);
-    if (partial) {
-        const double bs = block_sum((double)l21);
-        if (threadIdx.x == 0) partial[blockIdx.x] = bs;
-    }
-}
-
-// Chambolle-Pock primal pass (pass B).  VARIANT 0: ROF prox + over-relaxation (aux = xbar, out);
-// VARIANT 1: README loop (aux = y_f, in/out).
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int VARIANT>
-__global__ void __launch_bounds__(CTA_THREADS) cp_primal_kernel(FieldView<T> Y, T* __restrict__ x, T* __restrict__ aux, const T* __restrict__ x0,
-                                                                double* __restrict__ partial, Params<T> P, T tau, T c2, Tiling tl) {
-    const QuadIdx q = decode_quad(tl, P.Ni, VEC);
-    T fid = T(0);
-    if (q.active) {
-        if (VARIANT == 0)
-            fid = quad_cp_primal_rof<T, VEC, SCHEME, Z_ON, T_ON>(x, aux, x0, Y, P, tau, c2, q.z, q.t, q.i, q.j0);
-        else
-            fid = quad_cp_primal_readme<T, VEC, SCHEME, Z_ON, T_ON>(x, aux, x0, Y, P, tau, c2, q.z, q.t, q.i, q.j0);
-    }
-    if (partial) {
-        const double bs = block_sum((double)fid);
-        if (threadIdx.x == 0) partial[blockIdx.x] = bs;
     }
 }
 

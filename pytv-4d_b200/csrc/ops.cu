@@ -12,16 +12,11 @@ using namespace pytvb;
 
 namespace {
 
-bool use_gen2() {
-    const char* e = getenv("PYTVB_GEN");
-    return !e || atoi(e) >= 2;
-}
-
 template <typename T> struct DArgs { ImgView<T> X; T* D; Params<T> P; int vec; cudaStream_t st; };
 template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchD {
     static int run(const DArgs<T>& a) {
         {
-            if (use_gen2()) {
+            {
                 constexpr int R = PYTVB_STRIP_R;
                 const Tiling tl = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.P.Nz, VEC);
                 if (int rc = check_grid(tl)) return rc;
@@ -32,12 +27,6 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchD {
                 return PYTVB_OK;
             }
         }
-        const Tiling tl = make_tiling(a.P.Nj, a.P.Ni, a.P.M, 0, a.P.Nz, VEC);
-        if (int rc = check_grid(tl)) return rc;
-        D_kernel<T, VEC, SCHEME, Z, TT><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.D, a.P, tl);
-        count_launches(1);
-        PYTVB_CUDA(cudaGetLastError());
-        return PYTVB_OK;
     }
 };
 
@@ -45,7 +34,7 @@ template <typename T> struct DTArgs { FieldView<T> F; T* out; Params<T> P; cudaS
 template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchDT {
     static int run(const DTArgs<T>& a) {
         {
-            if (use_gen2()) {
+            {
                 constexpr int R = PYTVB_STRIP_R;
                 const Tiling tl = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.P.Nz, VEC);
                 if (int rc = check_grid(tl)) return rc;
@@ -56,12 +45,6 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchDT {
                 return PYTVB_OK;
             }
         }
-        const Tiling tl = make_tiling(a.P.Nj, a.P.Ni, a.P.M, 0, a.P.Nz, VEC);
-        if (int rc = check_grid(tl)) return rc;
-        DT_kernel<T, VEC, SCHEME, Z, TT><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(a.F, a.out, a.P, tl);
-        count_launches(1);
-        PYTVB_CUDA(cudaGetLastError());
-        return PYTVB_OK;
     }
 };
 
@@ -95,7 +78,7 @@ int run_l21(const pytvb_problem* pb, const void* D, int Nd, void* norms, double*
     P.sZf = P.sC * Nd;
     const int vec = pick_vec<T>(pb, {D, norms});
     double* partial = (double*)ws;
-    if (use_gen2()) {
+    {
         constexpr int R = PYTVB_STRIP_R;
         const Tiling tl = make_strip_tiling<R>(P.Nj, P.Ni, P.M, P.Nz, vec);
         if (int rc = check_grid(tl)) return rc;
@@ -107,15 +90,6 @@ int run_l21(const pytvb_problem* pb, const void* D, int Nd, void* norms, double*
         PYTVB_CUDA(cudaGetLastError());
         return finalize_sum(partial, tl.nblocks, d_sum, st);
     }
-    const Tiling tl = make_tiling(P.Nj, P.Ni, P.M, 0, P.Nz, vec);
-    if (int rc = check_grid(tl)) return rc;
-    if (vec == 1)
-        l21_kernel<T, 1><<<(unsigned)tl.nblocks, CTA_THREADS, 0, st>>>((const T*)D, Nd, (T*)norms, partial, P, tl);
-    else
-        l21_kernel<T, VecOf<T>::value><<<(unsigned)tl.nblocks, CTA_THREADS, 0, st>>>((const T*)D, Nd, (T*)norms, partial, P, tl);
-    count_launches(1);
-    PYTVB_CUDA(cudaGetLastError());
-    return finalize_sum(partial, tl.nblocks, d_sum, st);
 }
 
 }  // namespace

@@ -16,7 +16,7 @@
 #pragma once
 #include <cuda_fp16.h>
 
-#include "tv_core.cuh"
+#include "core.cuh"
 
 namespace pytvb {
 

@@ -12,11 +12,6 @@ using namespace pytvb;
 
 namespace {
 
-bool use_gen2() {
-    const char* e = getenv("PYTVB_GEN");
-    return !e || atoi(e) >= 2;
-}
-
 template <typename T> struct TvArgs {
     ImgView<T> X; ImgView<T> W; T* Wz0; T* G; T* norms; double* partial; Params<T> P; int z_lo, nz; cudaStream_t st;
     long long* nblocks_out;
@@ -25,7 +20,7 @@ template <typename T> struct TvArgs {
 template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchTv {
     static int run(const TvArgs<T>& a) {
         {
-            if (use_gen2()) {
+            {
                 constexpr int R = PYTVB_STRIP_R;
                 const Tiling t1 = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.nz, VEC, a.z_lo);
                 if (int rc = check_grid(t1)) return rc;
@@ -47,18 +42,6 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchTv {
                 return PYTVB_OK;
             }
         }
-        // sweep 1 over the slab plus the halo planes whose norms the sub-gradient reads
-        const Tiling t1 = make_tiling(a.P.Nj, a.P.Ni, a.P.M, a.z_lo, a.nz, VEC);
-        if (int rc = check_grid(t1)) return rc;
-        tv_norm_kernel<T, VEC, SCHEME, Z, TT><<<(unsigned)t1.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.Wz0, a.norms, a.partial, a.P, t1);
-        count_launches(1);
-        PYTVB_CUDA(cudaGetLastError());
-        *a.nblocks_out = t1.nblocks;
-        const Tiling t2 = make_tiling(a.P.Nj, a.P.Ni, a.P.M, 0, a.P.Nz, VEC);
-        tv_grad_kernel<T, VEC, SCHEME, Z, TT><<<(unsigned)t2.nblocks, CTA_THREADS, 0, a.st>>>(a.X, a.W, a.G, a.P, t2);
-        count_launches(1);
-        PYTVB_CUDA(cudaGetLastError());
-        return PYTVB_OK;
     }
 };
 

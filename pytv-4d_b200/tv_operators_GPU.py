@@ -33,11 +33,11 @@ def compute_L21_norm(D_img, return_array=False, return_pytorch_tensor=False):
     norms = torch.empty((Nz, M, Ni, Nj), dtype=d.dtype, device=d.device) if return_array else None
     _lib.check(_lib.lib().pytvb_l21(ctypes.byref(pb), _dev.ptr(d), Nd, _dev.ptr(norms), _dev.ptr(out), _dev.ptr(ws), _dev.stream_ptr()))
     l21 = out[0].to(d.dtype)
-    if not return_pytorch_tensor:
-        l21 = l21.cpu().numpy()
+    # the reference's return quirks (tv_operators_GPU.py:83-90): without return_array the scalar is ALWAYS a
+    # 0-d numpy array; with return_array it is a tensor only if return_pytorch_tensor, and the norm array is a tensor always
     if return_array:
-        return (l21, norms)
-    return l21
+        return (l21 if return_pytorch_tensor else l21.cpu().numpy(), norms)
+    return l21.cpu().numpy()
 
 
 def type_like(array, array_ref):

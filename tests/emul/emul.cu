@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE ONLY - never linked into libpytv_b200.so.
-// Runs the per-quad device functions of pytv-4d_b200/csrc/tv_core.cuh as HOST code, quad by quad, so that
+// Runs the per-quad device functions of pytv-4d_b200/csrc/strip_core.cuh (and the retired generation-1 code kept in
+// gen1_quad.cuh as a second statement of the arithmetic) as HOST code, quad by quad, so that
 // the index / boundary / halo / weighting logic of the CUDA kernels can be checked against the oracle in a
 // container that has no GPU.  Pointers in the problem descriptor and all arrays are HOST pointers here.
 #include <stdarg.h>
@@ -7,7 +8,7 @@
 
 #include "../../pytv-4d_b200/csrc/host_common.cuh"
 #include "../../pytv-4d_b200/csrc/strip_core.cuh"
-#include "../../pytv-4d_b200/csrc/kernels3.cuh"
+#include "gen1_quad.cuh"
 
 namespace pytvb {
 static char g_err[512];
@@ -241,73 +242,6 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct ETV2 {
     }
 };
 
-// generation 3: the ticket-ordered single-launch schedule of cp_fused_kernel, executed one ticket after the other.
-// Checks (returning a negative code on violation): every tile of both phases is visited exactly once, and when a
-// pass-B tile runs, the six pass-A groups it waits for on the device are already complete.
-template <typename T> struct FArgs {
-    Params<T> P; ImgView<T> Xin; FieldView<T> Y; T* y; T* x; T* aux; const T* x0; T sigma, lam, tau, c2; int variant, lag; double* sums;
-};
-template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct EFused {
-    static int run(const FArgs<T>& a) {
-        constexpr int R = 4;
-        const Tiling tl = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.P.Nz, VEC);
-        const FusedSched s = make_fused_sched(tl, a.P.Nz, (a.P.Ni + R - 1) / R, a.lag);
-        std::vector<unsigned> done((size_t)s.nbands * s.Nz, 0u);
-        std::vector<unsigned char> seen((size_t)s.total, 0);
-        const T c1 = T(1) / (T(1) + (a.variant == 0 ? a.tau : a.c2));
-        const T sig = a.sigma * a.P.inv_div;
-        double l21 = 0, fid = 0;
-        for (long long ticket = 0; ticket < s.total; ++ticket) {
-            const FusedTile f = fused_decode((unsigned)ticket, s);
-            if (f.band < 0 || f.band >= s.nbands || f.z < 0 || f.z >= s.Nz || f.t < 0 || f.t >= s.M || f.cb >= s.ncb || f.rbi >= s.RB) return -10;
-            const long long slot = ((long long)f.band * s.Nz + f.z) * s.G + ((f.t * s.RB + f.rbi) * s.ncb + f.cb);
-            const long long key = slot * 2 + f.phase;
-            if (key < 0 || key >= s.total || seen[key]) return -11;
-            seen[key] = 1;
-            if (f.phase == 1)
-                for (int db = -1; db <= 0; ++db)
-                    for (int dz = -1; dz <= 1; ++dz) {
-                        const int b = f.band + db, z = f.z + dz;
-                        if (b < 0 || z < 0 || z >= s.Nz) continue;
-                        if (done[(size_t)b * s.Nz + z] != s.G) return -12;
-                    }
-            for (int tid = 0; tid < CTA_THREADS; ++tid) {
-                const int tq = tid & (s.TW - 1), tr = tid >> s.tw_shift;
-                const int strip = (f.band * s.RB + f.rbi) * s.TR + tr;
-                const int qi = f.cb * s.TW + tq, j0 = qi * VEC;
-                if (!(strip < s.nstrips && qi < s.W)) continue;
-                if (f.phase == 0) {
-                    const DualPlane<T> pl = make_dual_plane<T, SCHEME>(a.Xin, a.y, a.P, f.z, f.t);
-                    for (int r = 0; r < R; ++r) {
-                        const int i = strip * R + r;
-                        if (i < a.P.Ni) {
-                            const int o = i * a.P.Nj + j0;
-                            l21 += (double)(a.P.tscale ? strip_quad_cp_dual<T, VEC, SCHEME, Z, TT, T, true>(pl, a.P, i, j0, o, i > 0 ? o - a.P.Nj : o, i < a.P.Ni - 1 ? o + a.P.Nj : o, sig, a.lam) : strip_quad_cp_dual<T, VEC, SCHEME, Z, TT, T, false>(pl, a.P, i, j0, o, i > 0 ? o - a.P.Nj : o, i < a.P.Ni - 1 ? o + a.P.Nj : o, sig, a.lam));
-                        }
-                    }
-                } else {
-                    const PrimalPlane<T> pl = make_primal_plane<T, SCHEME, Z, TT>(a.Y, a.P, f.z, f.t);
-                    const int i0 = strip * R - 1, nrows = (strip == s.nstrips - 1) ? R + 1 : R;
-                    for (int r = 0; r < nrows; ++r) {
-                        const int i = i0 + r;
-                        if (i >= 0 && i < a.P.Ni) {
-                            const int o = i * a.P.Nj + j0;
-                            const int ou = i > 0 ? o - a.P.Nj : o, od = i < a.P.Ni - 1 ? o + a.P.Nj : o;
-                            if (a.variant == 0) fid += (double)(a.P.tscale ? strip_quad_cp_primal<T, VEC, SCHEME, Z, TT, 0, false, T, true>(a.x, a.aux, a.x0, pl, a.P, i, j0, o, ou, od, a.tau, c1, a.c2) : strip_quad_cp_primal<T, VEC, SCHEME, Z, TT, 0, false, T, false>(a.x, a.aux, a.x0, pl, a.P, i, j0, o, ou, od, a.tau, c1, a.c2));
-                            else fid += (double)(a.P.tscale ? strip_quad_cp_primal<T, VEC, SCHEME, Z, TT, 1, false, T, true>(a.x, a.aux, a.x0, pl, a.P, i, j0, o, ou, od, a.tau, c1, a.c2) : strip_quad_cp_primal<T, VEC, SCHEME, Z, TT, 1, false, T, false>(a.x, a.aux, a.x0, pl, a.P, i, j0, o, ou, od, a.tau, c1, a.c2));
-                        }
-                    }
-                }
-            }
-            if (f.phase == 0) done[(size_t)f.band * s.Nz + f.z] += 1;
-        }
-        for (unsigned char v : seen) if (!v) return -13;
-        a.sums[0] = l21 * (double)a.P.inv_div;
-        a.sums[1] = fid;
-        return 0;
-    }
-};
-
 template <typename T> int vec_for(const pytvb_problem* pb, int force_scalar) {
     return (force_scalar || pb->Nj % VecOf<T>::value) ? 1 : VecOf<T>::value;
 }
@@ -479,25 +413,5 @@ extern "C" int pytvb_emulate_f16y(int op, const pytvb_problem* pb, const void* i
     return dispatch<EPrimalH, float>(vec, pb->scheme, ax.z_on, ax.t_on, a);
 }
 
-template <typename T>
-int run_fused_emul(const pytvb_problem* pb, int variant, const void* u, void* y, void* x, void* aux, const void* x0, double lam, double sigma, double tau,
-                   double c2, int lag, int force_scalar, const void* ilo, const void* ihi, const void* flo, const void* fhi, double* sums) {
-    const Axes ax = axes_of(pb);
-    FArgs<T> a;
-    a.P = make_params<T>(pb);
-    a.Xin = ImgView<T>{(const T*)u, (const T*)ilo, (const T*)ihi, 1};
-    a.Y = FieldView<T>{(const T*)y, (const T*)flo, (const T*)fhi};
-    a.y = (T*)y; a.x = (T*)x; a.aux = (T*)aux; a.x0 = (const T*)x0;
-    a.sigma = (T)sigma; a.lam = (T)lam; a.tau = (T)tau; a.c2 = (T)c2; a.variant = variant; a.lag = lag; a.sums = sums;
-    return dispatch<EFused, T>(vec_for<T>(pb, force_scalar), pb->scheme, ax.z_on, ax.t_on, a);
-}
-// sums[0] = L21(D u), sums[1] = |x_new - x0|^2; negative return = schedule violation (see EFused)
-extern "C" int pytvb_emulate_fused(const pytvb_problem* pb, int variant, const void* u, void* y, void* x, void* aux, const void* x0, double lam,
-                                   double sigma, double tau, double c2, int lag, int force_scalar, const void* ilo, const void* ihi, const void* flo,
-                                   const void* fhi, double* sums) {
-    if (check_problem(pb)) return -1;
-    return pb->dtype == PYTVB_F32 ? run_fused_emul<float>(pb, variant, u, y, x, aux, x0, lam, sigma, tau, c2, lag, force_scalar, ilo, ihi, flo, fhi, sums)
-                                  : run_fused_emul<double>(pb, variant, u, y, x, aux, x0, lam, sigma, tau, c2, lag, force_scalar, ilo, ihi, flo, fhi, sums);
-}
 extern "C" void pytvb_emulate_set_rows(int r) { g_emul_rows = (r == 4) ? 4 : 8; }
 extern "C" const char* pytvb_emulate_error(void) { return g_err; }

@@ -17,7 +17,7 @@ from pytv_b200 import _lib  # noqa: E402
 
 def build_emul(force=False):
     src = os.path.join(EMUL_DIR, "emul.cu")
-    deps = [src] + [os.path.join(ROOT, "pytv-4d_b200", "csrc", f) for f in ("tv_core.cuh", "strip_core.cuh", "kernels.cuh", "kernels2.cuh", "kernels3.cuh", "host_common.cuh")]
+    deps = [src] + [os.path.join(ROOT, "pytv-4d_b200", "csrc", f) for f in ("core.cuh", "strip_core.cuh", "kernels.cuh", "kernels2.cuh", "host_common.cuh")] + [os.path.join(EMUL_DIR, "gen1_quad.cuh")]
     if not force and os.path.exists(EMUL_SO) and all(os.path.getmtime(EMUL_SO) >= os.path.getmtime(d) for d in deps):
         return EMUL_SO
     cmd = ["nvcc", "-O1", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "--extended-lambda", "-gencode",
@@ -26,7 +26,7 @@ def build_emul(force=False):
     return EMUL_SO
 
 
-GEN = 1   # 1: tv_core.cuh quad code, 2: strip_core.cuh (module-level switch used by the tests)
+GEN = 1   # 1: tests/emul/gen1_quad.cuh (retired generation-1 code), 2: strip_core.cuh = what the library runs (module-level switch used by the tests)
 _h = None
 
 
@@ -147,23 +147,6 @@ def cp_primal_mirror(y, x, aux, x0, scheme, tau, c2, variant, lo, hi, mirror_pre
     pb, keep = _problem(scheme, x.dtype, x.shape, w.get("reg_z_over_reg", 1.0), w.get("reg_time", 0.0), w.get("mask_static", False),
                         w.get("factor_reg_static", 0.0), z_offset, Nz_global)
     return _call_mirror(1, pb, np.ascontiguousarray(y), x, aux, x0, lo, hi, mirror_prev, mirror_next, tau, c2, variant, scalar)
-
-
-def cp_fused(u, y, x, aux, x0, scheme, lam, sigma, tau, c2, variant, lag=3, scalar=False, ilo=None, ihi=None, flo=None, fhi=None, z_offset=0,
-             Nz_global=None, **w):
-    """One iteration through the emulated single-launch schedule (generation 3); returns (l21, fid)."""
-    pb, keep = _problem(scheme, x.dtype, x.shape, w.get("reg_z_over_reg", 1.0), w.get("reg_time", 0.0), w.get("mask_static", False),
-                        w.get("factor_reg_static", 0.0), z_offset, Nz_global)
-    h = emul()
-    VP = ctypes.c_void_p
-    h.pytvb_emulate_fused.restype = ctypes.c_int
-    h.pytvb_emulate_fused.argtypes = [ctypes.POINTER(_lib.Problem), ctypes.c_int, VP, VP, VP, VP, VP, ctypes.c_double, ctypes.c_double, ctypes.c_double,
-                                      ctypes.c_double, ctypes.c_int, ctypes.c_int, VP, VP, VP, VP, ctypes.POINTER(ctypes.c_double)]
-    sums = (ctypes.c_double * 2)()
-    rc = h.pytvb_emulate_fused(ctypes.byref(pb), variant, _ptr(u), _ptr(y), _ptr(x), _ptr(aux), _ptr(x0), lam, sigma, tau, c2, lag, int(scalar),
-                               _ptr(ilo), _ptr(ihi), _ptr(flo), _ptr(fhi), sums)
-    assert rc == 0, "fused schedule violation %d" % rc
-    return sums[0], sums[1]
 
 
 def cp_step_f16y(xbar, y_half, x, x0, scheme, lam, sigma, tau, theta, scalar=False, **w):

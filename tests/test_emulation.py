@@ -168,44 +168,6 @@ def test_cp_single_iteration_all_shapes(scheme, shape, gen):
         assert 0.5 * fid + 0.1 * l21 == pytest.approx(e_ref, rel=1e-12)
 
 
-@pytest.mark.parametrize("lag", [1, 3, 7])
-@pytest.mark.parametrize("shape", [(6, 2, 70, 8), (3, 1, 130, 12), (1, 1, 65, 4), (5, 1, 3, 8), (2, 2, 64, 8), (4, 2, 67, 1028)],
-                         ids=lambda s: "x".join(map(str, s)))
-@pytest.mark.parametrize("scheme", ["hybrid", "central", "upwind", "downwind"])
-def test_fused_single_launch_schedule(scheme, shape, lag):
-    """Generation 3: the ticket order of cp_fused_kernel executed sequentially - every tile once, every pass-B tile
-    after the six pass-A groups it depends on - reproduces the two-pass iteration (multi-band images, lagged rows)."""
-    if shape[3] > 1000 and (lag != 3 or scheme != "hybrid"):
-        pytest.skip("wide case once")
-    if scheme in ("upwind", "downwind") and lag == 7:
-        pytest.skip("lag > Nz is covered by the other schemes")
-    rs = np.random.RandomState(41)
-    Nz, M, Ni, Nj = shape
-    x0 = rs.rand(*shape)
-    kw = dict(reg_z_over_reg=0.6, reg_time=0.4)
-    Nd = orc.num_components(scheme, Nz, M, 0.6, 0.4)
-    y = 0.2 * rs.randn(Nz, Nd, M, Ni, Nj)
-    x = x0 + 0.1 * rs.randn(*shape)
-    xbar = x + 0.01 * rs.randn(*shape)
-    y_f = 0.1 * rs.randn(*shape)
-    # rof
-    x_ref, xb_ref, y_ref, e_ref = orc.cp_rof_step(x.copy(), xbar.copy(), x0, y.copy(), scheme, lam=0.1, sigma=0.5, tau=0.07, theta=0.9, **kw)
-    yy, xx, aux = y.copy(), x.copy(), xbar.copy()
-    l21, fid = em.cp_fused(aux, yy, xx, aux, x0, scheme, 0.1, 0.5, 0.07, 0.9, 0, lag=lag, **kw)
-    np.testing.assert_allclose(yy, y_ref, atol=1e-13)
-    np.testing.assert_allclose(xx, x_ref, atol=1e-13)
-    np.testing.assert_allclose(aux, xb_ref, atol=1e-13)
-    assert 0.5 * fid + 0.1 * l21 == pytest.approx(e_ref, rel=1e-12)
-    # readme (the dual pass differentiates x itself, which pass B overwrites in the same launch)
-    x_ref, yf_ref, y_ref, e_ref = orc.cp_readme_step(x.copy(), x0, y_f.copy(), y.copy(), scheme, lam=0.1, sigma_D=0.5, sigma_A=0.8, tau=0.07, **kw)
-    yy, xx, aux = y.copy(), x.copy(), y_f.copy()
-    l21, fid = em.cp_fused(xx, yy, xx, aux, x0, scheme, 0.1, 0.5, 0.07, 0.8, 1, lag=lag, **kw)
-    np.testing.assert_allclose(yy, y_ref, atol=1e-13)
-    np.testing.assert_allclose(xx, x_ref, atol=1e-13)
-    np.testing.assert_allclose(aux, yf_ref, atol=1e-13)
-    assert 0.5 * fid + 0.1 * l21 == pytest.approx(e_ref, rel=1e-12)
-
-
 @pytest.mark.parametrize("scalar", [False, True], ids=["vec", "scalar"])
 @pytest.mark.parametrize("scheme", SCHEMES)
 def test_half_precision_dual_storage(scheme, scalar):

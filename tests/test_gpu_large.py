@@ -92,24 +92,6 @@ def test_schemes_with_mask_on_C5_slab(scheme):
     _free()
 
 
-def test_fused_iteration_equals_two_pass_on_C4_slab():
-    """The single-launch iteration at the full benchmark size: bitwise equal state after 3 iterations."""
-    shape, kw = C4
-    torch.manual_seed(3)
-    x0 = torch.rand(shape, device="cuda") + 0.05 * torch.randn(shape, device="cuda")
-    a = pytv.CPSolver(x0, lam=0.1, scheme="hybrid", variant="rof", fused=False, **kw)
-    a.step(3)
-    xa, ea = a.x.clone(), a.energy()
-    y_a = a.y
-    b = pytv.CPSolver(x0, lam=0.1, scheme="hybrid", variant="rof", fused=True, **kw)
-    b.step(3)
-    assert b.energy() == pytest.approx(ea, rel=1e-6)
-    assert torch.equal(b.x, xa)
-    assert torch.equal(b.y, y_a)
-    del a, b, xa, y_a
-    _free()
-
-
 def test_cp_iteration_on_C4_slab_equals_two_half_slabs():
     """A whole-volume hybrid CP iteration is bitwise equal to the same iteration computed as two z-slabs with
     halo planes: the multi-GPU decomposition, exercised at full size on one GPU."""
@@ -158,7 +140,7 @@ def test_cp_passes_stay_at_the_hbm_roofline():
         peak = 6650.0
     torch.manual_seed(4)
     x0 = torch.rand(shape, device="cuda")
-    s = pytv.CPSolver(x0, lam=0.1, scheme="hybrid", variant="rof", fused=False, **kw)
+    s = pytv.CPSolver(x0, lam=0.1, scheme="hybrid", variant="rof", **kw)
     s.step(3)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     tA = tB = 0.0

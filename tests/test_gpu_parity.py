@@ -39,20 +39,6 @@ def _need_cuda():
     assert "B200" in torch.cuda.get_device_name(0) or True
 
 
-@pytest.fixture(params=["1", "2"], ids=["gen1", "gen2"], autouse=True)
-def gen(request):
-    """Every test runs against both kernel generations (PYTVB_GEN is read by the library at every call):
-    1 = one quad per thread (tv_core.cuh), 2 = strip kernels (strip_core.cuh, the default)."""
-    import os
-    old = os.environ.get("PYTVB_GEN")
-    os.environ["PYTVB_GEN"] = request.param
-    yield request.param
-    if old is None:
-        del os.environ["PYTVB_GEN"]
-    else:
-        os.environ["PYTVB_GEN"] = old
-
-
 # ------------------------------------------------------------------ golden vectors of the reference
 @pytest.mark.parametrize("case", [pytest.param(c, id=c["key"]) for c in cases.small_cases()])
 def test_small_goldens_float64(case, golden_small):
@@ -358,11 +344,6 @@ def test_time_weight_map(scheme, golden_small):
     """Extension (reference TODO, README.md:258): a (Nz,M,N,N) weight map of the time regularisation.  (1) the map
     where(mask, factor, 1) reproduces the reference's mask_static goldens; (2) a random map (with mask_static on top)
     matches the oracle for D, D_T, tv and CP, in float64 and float32; (3) adjointness."""
-    import os
-    if os.environ.get("PYTVB_GEN") == "1":
-        with pytest.raises(_lib.PytvError, match="generation-2"):
-            D_(scheme)(np.zeros((2, 2, 4, 4)), reg_time=1.0, time_weight=np.ones((2, 2, 4, 4)))
-        return
     case = [c for c in cases.small_cases() if c["key"] == "4x3x8/ztmask/" + scheme][0]
     x = cases.make_image(case)
     W = np.broadcast_to(np.where(cases.make_mask_static(case), case["fac"], 1.0), x.shape)
@@ -459,32 +440,6 @@ def test_cp_small4d_golden(scheme, dtype, golden_kat, gen):
     assert x[1, 1, 3, 4] == pytest.approx(g["rof_x_probe"], rel=1e-11 if dtype == np.float64 else 1e-4)
 
 
-@pytest.mark.parametrize("lag", ["1", "3"])
-@pytest.mark.parametrize("shape", [(6, 2, 70, 8), (3, 3, 130, 12), (1, 1, 65, 4), (5, 1, 3, 8), (9, 2, 67, 1028), (12, 4, 256, 256)],
-                         ids=lambda s: "x".join(map(str, s)))
-@pytest.mark.parametrize("scheme", SCHEMES)
-def test_fused_single_launch_iteration(scheme, shape, lag):
-    """Generation 3 (pass B lagging pass A inside one launch) is bitwise equal to the two-pass iteration, for both
-    forms, over several iterations (float32 and float64)."""
-    import os
-    os.environ["PYTVB_FUSED_LAG"] = lag
-    os.environ["PYTVB_GEN"] = "2"          # the single-launch kernel shares its per-quad code with generation 2
-    torch.manual_seed(41)
-    for dtype in (torch.float32, torch.float64):
-        x0 = torch.rand(shape, dtype=dtype, device="cuda")
-        for variant in ("rof", "readme"):
-            kw = dict(lam=0.1, scheme=scheme, variant=variant, reg_z_over_reg=0.6, reg_time=0.4)
-            a = pytv.CPSolver(x0, fused=False, **kw)
-            b = pytv.CPSolver(x0, fused=True, **kw)
-            assert b.fused
-            for _ in range(4):
-                a.step(); b.step()
-                # per-thread partial sums group different rows (pass B tiles sit one row higher): float rounding only
-                assert a.energy() == pytest.approx(b.energy(), rel=1e-6 if dtype == torch.float32 else 1e-12)
-            assert torch.equal(a.x, b.x) and torch.equal(a.y, b.y) and torch.equal(a.aux, b.aux)
-    del os.environ["PYTVB_FUSED_LAG"]
-
-
 @pytest.mark.parametrize("scheme", SCHEMES)
 def test_half_precision_dual_storage(scheme):
     """y stored as normalised IEEE half.  Not a parity path - the bound checked here is the one the
@@ -516,25 +471,6 @@ def test_half_precision_dual_storage(scheme):
     assert half.energy() == pytest.approx(ref.energy(), rel=1e-3)
     with pytest.raises(ValueError):
         pytv.CPSolver(x0.double(), dual_dtype=torch.float16, **kw)
-
-
-def test_cp_generations_agree_float32():
-    """gen-1 (exact sqrt / division) and gen-2 (rsqrt, reciprocal) float32 kernels stay within 1e-6 of each other
-    over 20 iterations on a 4-D volume large enough for many CTAs."""
-    import os
-    torch.manual_seed(4)
-    x0 = torch.rand(6, 3, 64, 128, device="cuda")
-    res = {}
-    saved = os.environ.get("PYTVB_GEN")
-    for g in ("1", "2"):
-        os.environ["PYTVB_GEN"] = g
-        s = pytv.CPSolver(x0, lam=0.1, scheme="hybrid", variant="rof", reg_time=2 ** -5)
-        s.step(20)
-        res[g] = (s.x.clone(), s.y.clone(), s.energy())
-    os.environ["PYTVB_GEN"] = saved
-    assert float((res["1"][0] - res["2"][0]).abs().max()) < 1e-5
-    assert float((res["1"][1] - res["2"][1]).abs().max()) < 1e-5
-    assert res["1"][2] == pytest.approx(res["2"][2], rel=1e-6)
 
 
 def test_cp_and_gd_loops_synthetic(golden_kat):

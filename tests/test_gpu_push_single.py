@@ -3,8 +3,6 @@ neighbours' halo planes) on ONE GPU: the "ranks" are z-slabs of one volume on th
 device buffers, and the passes of the slabs run one after the other on the stream (tests/p2p_schedule.py).  The result
 must equal the whole-volume iteration bit for bit.  The same schedule across two GPUs, with the planes in symmetric
 memory, is tests/test_gpu_multigpu.py."""
-import os
-
 import pytest
 import torch
 
@@ -12,17 +10,6 @@ import p2p_schedule
 from pytv_b200 import cp
 
 pytestmark = pytest.mark.gpu
-
-
-@pytest.fixture(autouse=True)
-def _generation_2():
-    old = os.environ.get("PYTVB_GEN")
-    os.environ["PYTVB_GEN"] = "2"       # the mirror stores live in the strip kernels
-    yield
-    if old is None:
-        del os.environ["PYTVB_GEN"]
-    else:
-        os.environ["PYTVB_GEN"] = old
 
 
 @pytest.mark.parametrize("variant", ["rof", "readme"])
