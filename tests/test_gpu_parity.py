@@ -158,6 +158,9 @@ def test_return_conventions():
     assert isinstance(l21, np.ndarray) and l21.shape == () and isinstance(arr, torch.Tensor)
     l21t, _ = opG.compute_L21_norm(opG.D_hybrid(x), return_array=True, return_pytorch_tensor=True)
     assert isinstance(l21t, torch.Tensor) and l21t.is_cuda
+    # without return_array the scalar is a 0-d numpy array even when a tensor is asked for (tv_operators_GPU.py:88-90)
+    l21n = opG.compute_L21_norm(opG.D_hybrid(x), return_array=False, return_pytorch_tensor=True)
+    assert isinstance(l21n, np.ndarray) and l21n.shape == ()
     assert float(l21) == pytest.approx(float(tv), rel=1e-6)
     np.testing.assert_allclose(arr.cpu().numpy(), np.where(np.isinf(n.cpu().numpy()), 0, n.cpu().numpy()), atol=1e-6)
     # errors
