@@ -53,7 +53,7 @@ class CudaSlabOps:
 
 
 class ShardedTV:
-    def __init__(self, scheme, group=None, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_reg_static=0, ops=None):
+    def __init__(self, scheme, group=None, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_reg_static=0, ops=None, comm=None):
         if scheme not in _dev.SCHEMES:
             raise ValueError("unknown scheme %r" % (scheme,))
         self.scheme = scheme
@@ -63,6 +63,7 @@ class ShardedTV:
         self.halo = HaloExchange(group)
         self._layout = None
         self._ms = None
+        self.transport = "nccl"
 
     # ---- slab placement: learned from the first call (every rank contributes its plane count)
     def _place(self, Nz_local, device):

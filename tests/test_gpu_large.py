@@ -154,3 +154,28 @@ def test_cp_passes_stay_at_the_hbm_roofline():
     del s
     _free()
     assert fracA > 0.85 and fracB > 0.85, (fracA, fracB)
+
+
+def test_cp_float32_against_oracle_at_benchmark_plane_size():
+    """The float32 iteration the benchmark times (hybrid, reg_time = 2^-5, planes 1024 x 1024, M = 4) against the float64
+    oracle on a reduced slab: 5 CP-ROF iterations, energy 1e-5 relative, x 1e-5 absolute (the north-star tolerances).
+    bench.py runs the same comparison (against the reference's own numpy code) as its parity gate before it times anything."""
+    import numpy as np
+    from oracle import tv_oracle as orc
+    shape, kw = (2, 4, 1024, 1024), dict(reg_time=2 ** -5)
+    rs = np.random.RandomState(11)
+    x0 = (rs.rand(*shape) + 0.05 * rs.randn(*shape)).astype(np.float32)
+    s = pytv.CPSolver(torch.from_numpy(x0).cuda(), lam=0.1, scheme="hybrid", variant="rof", **kw)
+    x = xb = x0.astype(np.float64)
+    x064 = x0.astype(np.float64)
+    y = np.zeros((shape[0], 8) + shape[1:])
+    for _ in range(5):
+        s.step()
+        x, xb, y, e = orc.cp_rof_step(x, xb, x064, y, "hybrid", lam=0.1, sigma=0.5, tau=s.tau, theta=1.0, **kw)
+        assert abs(s.energy() - e) <= 1e-5 * abs(e)
+    assert float(np.abs(s.x.cpu().numpy() - x).max()) <= 1e-5
+    assert float(np.abs(s.y.cpu().numpy() - y).max()) <= 1e-5
+    tv, G = tvG.tv_hybrid(s.x, return_pytorch_tensor=True, **kw)
+    tv_o, G_o = orc.tv(x, "hybrid", **kw)
+    assert abs(float(tv) - tv_o) <= 1e-5 * tv_o
+    _free()
