@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PYTVB_VERSION 100 /* 0.1.0 */
+#define PYTVB_VERSION 101 /* 0.1.1: pytvb_problem grew time_scale_lo / time_scale_hi; the single-launch iteration was removed */
 
 typedef enum { PYTVB_OK = 0, PYTVB_ERR_ARG = -1, PYTVB_ERR_CUDA = -2 } pytvb_status;
 
@@ -54,6 +54,8 @@ typedef struct pytvb_problem {
     const uint8_t* mask_static; /* device (Ni, Nj) bytes, nonzero = static pixel; NULL = none */
     const void* time_scale;     /* EXTENSION (reference TODO, README.md:258): device (Nz, M, Ni, Nj) array of `dtype`, the per-voxel factor
                                  * of the time component(s) = sqrt of a weight map; multiplies on top of mask_static; NULL = none. */
+    const void* time_scale_lo;  /* slabs with z halos, pytvb_tv only: the (M, Ni, Nj) plane of time_scale at local z = -1 / z = Nz (the */
+    const void* time_scale_hi;  /* gradient norm of the neighbouring plane enters the sub-gradient); NULL where the slab touches the volume edge */
 } pytvb_problem;
 
 int pytvb_version(void);
@@ -64,7 +66,8 @@ uint64_t pytvb_launch_count(void);
 /* Number of difference components Nd (tv_operators_CPU.py:110-114 hybrid: 4/6/8; :256-260 others: 2/3/4). */
 int pytvb_num_components(const pytvb_problem* pb);
 
-/* Scratch sizes.  `reduce`: needed by every call that produces a scalar; `tv`: needed by pytvb_tv. */
+/* Scratch sizes.  `reduce`: needed by every call that produces a scalar; `tv`: needed by pytvb_tv (a few bytes when the
+ * single-sweep kernel takes the problem, an (Nz+2)-plane inverse-norm field for the two-sweep fallback). */
 size_t pytvb_reduce_workspace_bytes(const pytvb_problem* pb);
 size_t pytvb_tv_workspace_bytes(const pytvb_problem* pb);
 
@@ -86,9 +89,17 @@ int pytvb_apply_mask(const pytvb_problem* pb, void* x, const uint8_t* mask, int 
 
 /* tv_<scheme>(img) (tv_GPU.py:47,142,217,290): d_tv[0] = TV (device double), G = the reference's
  * sub-gradient, norms_or_null = gradient norms with inf where zero (return_grad_norms).
- * halo_lo2 / halo_hi2: TWO image planes each (2,M,Ni,Nj): z = -2,-1 and z = Nz, Nz+1. */
+ * halo_lo2 / halo_hi2: TWO image planes each (2,M,Ni,Nj): z = -2,-1 and z = Nz, Nz+1.
+ * One launch: a z-marching tile kernel reads x once and writes G once (8 bytes per voxel; csrc/tile_core.cuh).  The
+ * two-sweep form (inverse norms through a workspace) remains for the cases the tile kernel does not take: more than 16
+ * coupled time frames, and the centred scheme on a length-2 z or time axis. */
 int pytvb_tv(const pytvb_problem* pb, const void* x, void* G, void* norms_or_null, double* d_tv, const void* halo_lo2,
              const void* halo_hi2, void* ws_reduce, void* ws_tv, void* stream);
+
+/* One step of the README's sub-gradient descent (README.md:120-123), fused: x <- x - step * ((x - x0) + lam * G) with G from
+ * pytvb_tv, and d_fid_or_null[0] = sum (x_new - x0)^2 (the data term of the loss, README.md:123). */
+int pytvb_gd_update(const pytvb_problem* pb, void* x, const void* x0, const void* G, double step, double lam, double* d_fid_or_null, void* ws,
+                    void* stream);
 
 /* TV value only, d_tv[0] = L21(D_<scheme>(x)) without materialising D or the sub-gradient (one read of x):
  * the TV term of a primal energy / duality gap.  halos: as pytvb_D (ONE image plane each side). */
@@ -118,8 +129,7 @@ int pytvb_cp_primal_readme(const pytvb_problem* pb, const void* y_tv, void* x, v
  * previous / next rank, or NULL.  Pass A pushes the backward-type z component of local plane 0 (the previous rank's field
  * halo_hi) and the forward-type z component of the last plane (the next rank's field halo_lo); pass B pushes plane 0 / the last
  * plane of the image the next dual pass differentiates (xbar for variant 0, x for variant 1) into the neighbours' image halo_hi /
- * halo_lo.  The caller separates the passes with a cross-rank barrier on the stream (no data moves in it).  Not combinable with
- * time_scale. */
+ * halo_lo.  The caller separates the passes with a cross-rank barrier on the stream (no data moves in it). */
 int pytvb_cp_dual_p2p(const pytvb_problem* pb, const void* xbar, void* y, double lam, double sigma, double* d_l21_or_null,
                       const void* halo_lo, const void* halo_hi, void* mirror_prev, void* mirror_next, void* ws, void* stream);
 int pytvb_cp_primal_p2p(const pytvb_problem* pb, int variant, const void* y, void* x, void* aux, const void* x0, double tau, double c2,
@@ -139,7 +149,7 @@ int pytvb_cp_primal_rof_f16y(const pytvb_problem* pb, const void* y_half, void* 
 /* ---- host-buffer entry points: what a caller without device memory management binds -------------------
  * tv_<scheme> with numpy-style HOST arrays in and out (the reference's default call: numpy in, numpy out,
  * tv_GPU.py:129-139).  Copies x to the device, runs pytvb_tv, copies G (and norms) back, returns TV. */
-int pytvb_tv_host(const pytvb_problem* pb_host_mask /* mask_static is a HOST pointer here */, const void* x_host, void* G_host,
+int pytvb_tv_host(const pytvb_problem* pb_host_mask /* mask_static and time_scale are HOST pointers here */, const void* x_host, void* G_host,
                   void* norms_host_or_null, double* tv_out);
 
 /* Streaming Chambolle-Pock denoiser with device-resident state (x, xbar, y) and HOST data in / out. */

@@ -30,6 +30,8 @@ class Problem(ctypes.Structure):
         ("factor_reg_static", ctypes.c_double),
         ("mask_static", ctypes.c_void_p),
         ("time_scale", ctypes.c_void_p),
+        ("time_scale_lo", ctypes.c_void_p),
+        ("time_scale_hi", ctypes.c_void_p),
     ]
 
 
@@ -40,7 +42,7 @@ def make_problem(scheme, dtype_id, shape, reg_z_over_reg=1.0, reg_time=0.0, fact
     return Problem(SCHEME_ID[scheme] if isinstance(scheme, str) else int(scheme), int(dtype_id), Nz, M, Ni, Nj, int(z_offset),
                    int(Nz if Nz_global is None else Nz_global), rz, float(reg_time), float(factor_reg_static),
                    ctypes.c_void_p(mask_static_ptr) if mask_static_ptr else None,
-                   ctypes.c_void_p(time_scale_ptr) if time_scale_ptr else None)
+                   ctypes.c_void_p(time_scale_ptr) if time_scale_ptr else None, None, None)
 
 
 _VP = ctypes.c_void_p
@@ -57,6 +59,7 @@ _PROTOTYPES = {
     "pytvb_l21": (ctypes.c_int, [_PB, _VP, ctypes.c_int64, _VP, _VP, _VP, _VP]),
     "pytvb_apply_mask": (ctypes.c_int, [_PB, _VP, _VP, ctypes.c_int, _VP]),
     "pytvb_tv": (ctypes.c_int, [_PB, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "pytvb_gd_update": (ctypes.c_int, [_PB, _VP, _VP, _VP, ctypes.c_double, ctypes.c_double, _VP, _VP, _VP]),
     "pytvb_tv_value": (ctypes.c_int, [_PB, _VP, _VP, _VP, _VP, _VP, _VP]),
     "pytvb_cp_dual": (ctypes.c_int, [_PB, _VP, _VP, ctypes.c_double, ctypes.c_double, _VP, _VP, _VP, _VP, _VP]),
     "pytvb_cp_primal_rof": (ctypes.c_int, [_PB, _VP, _VP, _VP, _VP, ctypes.c_double, ctypes.c_double, _VP, _VP, _VP, _VP, _VP]),

@@ -155,11 +155,32 @@ class HaloExchange:
             self._reduce_group = self.dist.new_group(ranks=list(range(self.dist.get_world_size())))
 
 
+def neighbour_handshake(hdl, prev, nxt, timeout_ms, sync="auto"):
+    """Device-side fence between z-NEIGHBOURS on the current stream (no data): "everything I stored into your halo buffers
+    so far is visible" to both neighbours, then wait for the same from them.  Signals travel through the signal pads of the
+    symmetric-memory allocation `hdl` (put_signal / wait_signal: one flag per (channel, source rank), set by the sender
+    once the receiver has consumed the previous one).  A rank is therefore at most one pass ahead of its neighbours - which
+    is also what makes it safe for them to overwrite its halo planes in their next pass - and a slow rank delays only its
+    neighbours by one pass instead of stalling the whole group at a barrier.  All puts precede all waits on every rank, so
+    the pattern cannot deadlock.  sync="barrier" (or a torch without put_signal) uses the group-wide barrier instead."""
+    if sync == "barrier" or not hasattr(hdl, "put_signal"):
+        hdl.barrier(channel=0, timeout_ms=timeout_ms)
+        return
+    if nxt is not None:
+        hdl.put_signal(nxt, channel=1, timeout_ms=timeout_ms)
+    if prev is not None:
+        hdl.put_signal(prev, channel=2, timeout_ms=timeout_ms)
+    if prev is not None:
+        hdl.wait_signal(prev, channel=1, timeout_ms=timeout_ms)
+    if nxt is not None:
+        hdl.wait_signal(nxt, channel=2, timeout_ms=timeout_ms)
+
+
 class PeerHalos:
     """The four halo planes of a rank, [img_lo, img_hi, fld_lo, fld_hi], in symmetric memory (torch.distributed.
     _symmetric_memory: cuMem allocations mapped into every rank of the node over NVLink).  The passes of the
     neighbouring ranks store into these planes directly (`peer`), the local passes read them (`local`); `barrier` is
-    the cross-rank fence between passes (a one-CTA kernel on the current stream, no data)."""
+    the fence between passes: a device-side handshake with the two z-neighbours only (neighbour_handshake)."""
     IMG_LO, IMG_HI, FLD_LO, FLD_HI = 0, 1, 2, 3
 
     def __init__(self, halo, plane, dtype, device):
@@ -170,6 +191,9 @@ class PeerHalos:
         self.buf.zero_()
         self.plane_bytes = self.buf[0].numel() * self.buf.element_size()
         self.timeout_ms = int(os.environ.get("PYTVB_P2P_TIMEOUT_MS", "60000"))   # a lost rank traps instead of hanging the GPU
+        self.sync = os.environ.get("PYTVB_P2P_SYNC", "auto")                      # "barrier": the group-wide fence of round 1 (A/B runs)
+        self.prev, self.next = halo.prev, halo.next
+        self.hdl.barrier(channel=0, timeout_ms=self.timeout_ms)                  # everyone has zeroed its planes and signal pads are idle
 
     def local(self, slot):
         return self.buf[slot]
@@ -179,7 +203,7 @@ class PeerHalos:
         return None if rank is None else int(self.hdl.buffer_ptrs[rank]) + slot * self.plane_bytes
 
     def barrier(self):
-        self.hdl.barrier(channel=0, timeout_ms=self.timeout_ms)
+        neighbour_handshake(self.hdl, self.prev, self.next, self.timeout_ms, self.sync)
 
 
 class CPSolver:
@@ -191,8 +215,8 @@ class CPSolver:
     comm : how the one-plane halos travel between z-neighbours.  "p2p": the pass kernels store their boundary planes
            straight into the neighbour's halo buffers (symmetric memory over NVLink, one node), a device-side barrier
            separates the passes; "nccl": batched isend/irecv before each pass; "auto" (default, or the environment
-           variable PYTVB_COMM): p2p where every rank can set it up, else nccl.  Half-precision duals, time_weight and
-           injected executors always use nccl.
+           variable PYTVB_COMM): p2p where every rank can set it up, else nccl.  Half-precision duals and injected
+           executors always use nccl.
     """
 
     def __init__(self, x0, lam, scheme="hybrid", variant="rof", sigma=0.5, tau=None, theta=1.0, sigma_A=1.0, reg_z_over_reg=1.0,
@@ -302,10 +326,10 @@ class CPSolver:
             interior_lo, interior_hi = self.halo.prev is not None, self.halo.next is not None
             need_img_lo, need_img_hi = scheme != "upwind", scheme != "downwind"
             need_fld_lo, need_fld_hi = scheme != "downwind", scheme != "upwind"
-            p2p_ok = (ops is None and self._ts is None and self.dual_dtype == dt and not self.overlap
+            p2p_ok = (ops is None and self.dual_dtype == dt and not self.overlap
                       and str(self.halo.dist.get_backend(self.halo.group)).lower() == "nccl")
             if comm == "p2p" and not p2p_ok:
-                raise ValueError("comm='p2p' needs the CUDA executor over an NCCL group, the blocking schedule, no time_weight and full-precision duals")
+                raise ValueError("comm='p2p' needs the CUDA executor over an NCCL group, the blocking schedule and full-precision duals")
             if comm != "nccl" and p2p_ok:
                 # measured on 8 x B200 (profiles/r01zb_*): 9.86 ms per iteration against 10.18 ms with send/recv (one GPU: 9.60)
                 try:

@@ -4,6 +4,7 @@
 #include <atomic>
 
 #include "host_common.cuh"
+#include "tv_path.cuh"
 
 namespace pytvb {
 static thread_local char g_err[512] = "";
@@ -32,13 +33,17 @@ int pytvb_num_components(const pytvb_problem* pb) {
 
 size_t pytvb_reduce_workspace_bytes(const pytvb_problem* pb) {
     if (check_problem(pb) != PYTVB_OK) return 0;
-    return (size_t)(max_partials(pb) + REDUCE_STAGE2) * sizeof(double);
+    long long n = max_partials(pb);
+    const long long nt = tile_max_blocks(pb);
+    if (nt > n) n = nt;
+    return (size_t)(n + REDUCE_STAGE2) * sizeof(double);
 }
 
 size_t pytvb_tv_workspace_bytes(const pytvb_problem* pb) {
     if (check_problem(pb) != PYTVB_OK) return 0;
+    if (tv_uses_tile(pb)) return 256;   // single-sweep kernel: nothing goes through memory
     const size_t es = pb->dtype == PYTVB_F32 ? 4 : 8;
-    // inverse-norm field for the slab plus one plane on each side
+    // two-sweep fallback: inverse-norm field for the slab plus one plane on each side
     return (size_t)(pb->Nz + 2) * pb->M * pb->Ni * pb->Nj * es + 256;
 }
 

@@ -21,9 +21,12 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchDual {
                 const Tiling tl = make_strip_tiling<R>(a.P.Nj, a.P.Ni, a.P.M, a.P.Nz, VEC);
                 if (int rc = check_grid(tl)) return rc;
                 if (Z && (a.mir_prev || a.mir_next)) {
-                    PYTVB_REQUIRE(!a.P.tscale, "peer-memory halo push and time_scale cannot be combined");
-                    cp_dual_strip_kernel<T, VEC, SCHEME, Z, TT, R, T, false, Z><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(
-                        a.Xb, a.y, a.partial, a.P, a.sigma * a.P.inv_div, a.lam, tl, MirrorBufs<T>{a.mir_prev, a.mir_next});
+                    if (TT && a.P.tscale)
+                        cp_dual_strip_kernel<T, VEC, SCHEME, Z, TT, R, T, TT, Z><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(
+                            a.Xb, a.y, a.partial, a.P, a.sigma * a.P.inv_div, a.lam, tl, MirrorBufs<T>{a.mir_prev, a.mir_next});
+                    else
+                        cp_dual_strip_kernel<T, VEC, SCHEME, Z, TT, R, T, false, Z><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(
+                            a.Xb, a.y, a.partial, a.P, a.sigma * a.P.inv_div, a.lam, tl, MirrorBufs<T>{a.mir_prev, a.mir_next});
                 } else if (TT && a.P.tscale) cp_dual_strip_kernel<T, VEC, SCHEME, Z, TT, R, T, TT><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(
                     a.Xb, a.y, a.partial, a.P, a.sigma * a.P.inv_div, a.lam, tl);
                 else cp_dual_strip_kernel<T, VEC, SCHEME, Z, TT, R, T, false><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(
@@ -49,10 +52,16 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchPrimal 
                 if (int rc = check_grid(tl)) return rc;
                 const T c1 = T(1) / (T(1) + (a.variant == 0 ? a.tau : a.c2));
                 if (Z && (a.mir_prev || a.mir_next)) {
-                    PYTVB_REQUIRE(!a.P.tscale, "peer-memory halo push and time_scale cannot be combined");
                     const MirrorBufs<T> mb{a.mir_prev, a.mir_next};
-                    if (a.variant == 0)
+                    const bool ts = TT && a.P.tscale;
+                    if (a.variant == 0 && ts)
+                        cp_primal_strip_kernel<T, VEC, SCHEME, Z, TT, 0, R, T, TT, Z><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(
+                            a.Y, a.x, a.aux, a.x0, a.partial, a.P, a.tau, c1, a.c2, tl, T(-1), mb);
+                    else if (a.variant == 0)
                         cp_primal_strip_kernel<T, VEC, SCHEME, Z, TT, 0, R, T, false, Z><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(
+                            a.Y, a.x, a.aux, a.x0, a.partial, a.P, a.tau, c1, a.c2, tl, T(-1), mb);
+                    else if (ts)
+                        cp_primal_strip_kernel<T, VEC, SCHEME, Z, TT, 1, R, T, TT, Z><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(
                             a.Y, a.x, a.aux, a.x0, a.partial, a.P, a.tau, c1, a.c2, tl, T(-1), mb);
                     else
                         cp_primal_strip_kernel<T, VEC, SCHEME, Z, TT, 1, R, T, false, Z><<<(unsigned)tl.nblocks, CTA_THREADS, 0, a.st>>>(

@@ -17,14 +17,22 @@ struct DeviceBuf {
     cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
 };
 
-// Device copy of a host (Ni,Nj) byte mask; dev problem = host problem with the pointer swapped.
-int upload_mask(const pytvb_problem* host_pb, pytvb_problem* dev_pb, DeviceBuf* buf, cudaStream_t st) {
+// Device copies of the HOST arrays a problem descriptor points to - the (Ni,Nj) byte mask and the (Nz,M,Ni,Nj) time scale;
+// dev problem = host problem with the pointers swapped.
+int upload_mask(const pytvb_problem* host_pb, pytvb_problem* dev_pb, DeviceBuf* buf, DeviceBuf* ts_buf, cudaStream_t st) {
     *dev_pb = *host_pb;
+    dev_pb->time_scale_lo = dev_pb->time_scale_hi = nullptr;      // whole volumes only
     if (host_pb->mask_static) {
         const size_t n = (size_t)host_pb->Ni * host_pb->Nj;
         PYTVB_CUDA(buf->alloc(n));
         PYTVB_CUDA(cudaMemcpyAsync(buf->p, host_pb->mask_static, n, cudaMemcpyHostToDevice, st));
         dev_pb->mask_static = (const uint8_t*)buf->p;
+    }
+    if (host_pb->time_scale) {
+        const size_t n = voxels(host_pb) * elem_size(host_pb);
+        PYTVB_CUDA(ts_buf->alloc(n));
+        PYTVB_CUDA(cudaMemcpyAsync(ts_buf->p, host_pb->time_scale, n, cudaMemcpyHostToDevice, st));
+        dev_pb->time_scale = ts_buf->p;
     }
     return PYTVB_OK;
 }
@@ -34,7 +42,7 @@ int upload_mask(const pytvb_problem* host_pb, pytvb_problem* dev_pb, DeviceBuf* 
 struct pytvb_cp_solver {
     pytvb_problem pb;          // device-side problem (mask_static on the device)
     double lam, sigma, tau, theta;
-    DeviceBuf mask, x, xbar, x0, y, ws, scal;
+    DeviceBuf mask, tscale, x, xbar, x0, y, ws, scal;
     cudaStream_t st = nullptr;
     size_t img_bytes = 0, y_bytes = 0;
     ~pytvb_cp_solver() { if (st) cudaStreamDestroy(st); }
@@ -46,12 +54,11 @@ int pytvb_tv_host(const pytvb_problem* pb, const void* x_host, void* G_host, voi
     if (int rc = check_problem(pb)) return rc;
     PYTVB_REQUIRE(x_host && G_host && tv_out, "x_host, G_host and tv_out must not be NULL");
     PYTVB_REQUIRE(pb->z_offset == 0 && pb->Nz_global == pb->Nz, "pytvb_tv_host works on whole volumes");
-    PYTVB_REQUIRE(!pb->time_scale, "time_scale is not supported by the host-buffer entry points");
     cudaStream_t st = nullptr;
     const size_t nb = voxels(pb) * elem_size(pb);
-    DeviceBuf mask, x, G, norms, wsr, wst, dtv;
+    DeviceBuf mask, tscale, x, G, norms, wsr, wst, dtv;
     pytvb_problem dpb;
-    if (int rc = upload_mask(pb, &dpb, &mask, st)) return rc;
+    if (int rc = upload_mask(pb, &dpb, &mask, &tscale, st)) return rc;
     PYTVB_CUDA(x.alloc(nb));
     PYTVB_CUDA(G.alloc(nb));
     if (norms_host_or_null) PYTVB_CUDA(norms.alloc(nb));
@@ -71,14 +78,13 @@ int pytvb_cp_create(const pytvb_problem* pb, double lam, double sigma, double ta
     if (int rc = check_problem(pb)) return rc;
     PYTVB_REQUIRE(out, "out must not be NULL");
     PYTVB_REQUIRE(pb->z_offset == 0 && pb->Nz_global == pb->Nz, "the host-buffer solver works on whole volumes");
-    PYTVB_REQUIRE(!pb->time_scale, "time_scale is not supported by the host-buffer entry points");
     PYTVB_REQUIRE(lam >= 0 && sigma > 0 && tau > 0, "lam >= 0, sigma > 0, tau > 0 required");
     pytvb_cp_solver* s = new (std::nothrow) pytvb_cp_solver();
     PYTVB_REQUIRE(s, "out of host memory");
     s->lam = lam; s->sigma = sigma; s->tau = tau; s->theta = theta;
     cudaError_t e = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete s; set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e)); return PYTVB_ERR_CUDA; }
-    int rc = upload_mask(pb, &s->pb, &s->mask, s->st);
+    int rc = upload_mask(pb, &s->pb, &s->mask, &s->tscale, s->st);
     s->img_bytes = voxels(pb) * elem_size(pb);
     s->y_bytes = s->img_bytes * (size_t)axes_of(pb).Nd;
     if (rc == PYTVB_OK) {

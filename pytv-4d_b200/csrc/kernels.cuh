@@ -150,4 +150,24 @@ __global__ void __launch_bounds__(CTA_THREADS) apply_mask_kernel(T* __restrict__
     }
 }
 
+// Sub-gradient descent update of the README loop (README.md:120-123), fused: x <- x - step * ((x - x0) + lam * G) and the
+// fidelity partial sums sum (x_new - x0)^2, one read of x, x0, G and one write of x.
+template <typename T>
+__global__ void __launch_bounds__(CTA_THREADS) gd_update_kernel(T* __restrict__ x, const T* __restrict__ x0, const T* __restrict__ G, long long V, T step,
+                                                                T lam, double* __restrict__ partial) {
+    const long long stride = (long long)gridDim.x * CTA_THREADS;
+    T fid = T(0);
+    for (long long k = (long long)blockIdx.x * CTA_THREADS + threadIdx.x; k < V; k += stride) {
+        const T xo = x[k], d0 = x0[k];
+        const T xn = xo - step * ((xo - d0) + lam * G[k]);
+        x[k] = xn;
+        const T r = xn - d0;
+        fid += r * r;
+    }
+    if (partial) {
+        const double bs = block_sum((double)fid);
+        if (threadIdx.x == 0) partial[blockIdx.x] = bs;
+    }
+}
+
 }  // namespace pytvb

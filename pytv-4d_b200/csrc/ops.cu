@@ -121,6 +121,25 @@ int pytvb_l21(const pytvb_problem* pb, const void* D, int64_t Nd, void* norms_or
                                   : run_l21<double>(pb, D, (int)Nd, norms_or_null, d_sum, ws, st);
 }
 
+int pytvb_gd_update(const pytvb_problem* pb, void* x, const void* x0, const void* G, double step, double lam, double* d_fid_or_null, void* ws,
+                    void* stream) {
+    if (int rc = check_problem(pb)) return rc;
+    PYTVB_REQUIRE(x && x0 && G, "x, x0 and G must not be NULL");
+    PYTVB_REQUIRE(!d_fid_or_null || ws, "a reduction workspace is required when d_fid is requested");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long V = (long long)pb->Ni * pb->Nj * pb->M * pb->Nz;
+    long long nb = (V + CTA_THREADS - 1) / CTA_THREADS;
+    if (nb > 148 * 8) nb = 148 * 8;
+    double* partial = d_fid_or_null ? (double*)ws : nullptr;
+    if (pb->dtype == PYTVB_F32)
+        gd_update_kernel<float><<<(unsigned)nb, CTA_THREADS, 0, st>>>((float*)x, (const float*)x0, (const float*)G, V, (float)step, (float)lam, partial);
+    else
+        gd_update_kernel<double><<<(unsigned)nb, CTA_THREADS, 0, st>>>((double*)x, (const double*)x0, (const double*)G, V, step, lam, partial);
+    count_launches(1);
+    PYTVB_CUDA(cudaGetLastError());
+    return d_fid_or_null ? finalize_sum(partial, nb, d_fid_or_null, st) : PYTVB_OK;
+}
+
 int pytvb_apply_mask(const pytvb_problem* pb, void* x, const uint8_t* mask, int mask_is_plane, void* stream) {
     if (int rc = check_problem(pb)) return rc;
     PYTVB_REQUIRE(x && mask, "x and mask must not be NULL");

@@ -3,6 +3,8 @@
 
 #include "host_common.cuh"
 #include "kernels2.cuh"
+#include "tv_path.cuh"
+#include "tv_args.cuh"
 
 #ifndef PYTVB_STRIP_R
 #define PYTVB_STRIP_R 8
@@ -11,12 +13,8 @@
 using namespace pytvb;
 
 namespace {
-
-template <typename T> struct TvArgs {
-    ImgView<T> X; ImgView<T> W; T* Wz0; T* G; T* norms; double* partial; Params<T> P; int z_lo, nz; cudaStream_t st;
-    long long* nblocks_out;
-};
-
+// (the single-sweep tile kernel is launched from tv_tile.cu - its own translation unit, so that its kernel variants compile in
+// parallel with the two-sweep fallback's: run_tv_tile, declared in tv_args.cuh)
 template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchTv {
     static int run(const TvArgs<T>& a) {
         {
@@ -66,8 +64,14 @@ int run_tv(const pytvb_problem* pb, const void* x, void* G, void* norms, double*
     a.st = st;
     long long nblocks = 0;
     a.nblocks_out = &nblocks;
-    const int vec = pick_vec<T>(pb, {x, G, norms, lo2, hi2});
-    if (int rc = dispatch<LaunchTv, T>(vec, pb->scheme, ax.z_on, ax.t_on, a)) return rc;
+    a.TS = ImgView<T>{a.P.tscale, (const T*)pb->time_scale_lo, (const T*)pb->time_scale_hi, 1};
+    const int vec = pick_vec<T>(pb, {x, G, norms, lo2, hi2, pb->time_scale_lo, pb->time_scale_hi});
+    if (tv_uses_tile(pb)) {
+        if (int rc = run_tv_tile<T>(vec, pb->scheme, ax.z_on, ax.t_on, a)) return rc;
+    } else {
+        PYTVB_REQUIRE(!(pb->time_scale && (lo2 || hi2)), "time_scale on slabs with z halos needs the single-sweep kernel (not this problem: > 16 coupled frames or a centred length-2 axis)");
+        if (int rc = dispatch<LaunchTv, T>(vec, pb->scheme, ax.z_on, ax.t_on, a)) return rc;
+    }
     return finalize_sum(a.partial, nblocks, d_tv, st);
 }
 
@@ -120,7 +124,10 @@ extern "C" int pytvb_tv(const pytvb_problem* pb, const void* x, void* G, void* n
                         const void* halo_hi2, void* ws_reduce, void* ws_tv, void* stream) {
     if (int rc = check_problem(pb)) return rc;
     PYTVB_REQUIRE(x && G && d_tv && ws_reduce && ws_tv, "x, G, d_tv and the workspaces must not be NULL");
-    PYTVB_REQUIRE(!(pb->time_scale && (halo_lo2 || halo_hi2)), "time_scale is not available for slabs with z halos in pytvb_tv");
+    if (pb->time_scale && axes_of(pb).z_on && axes_of(pb).t_on) {
+        PYTVB_REQUIRE(!(halo_lo2 && !pb->time_scale_lo), "slab starts inside the volume: time_scale_lo (the scale's plane z = -1) is required");
+        PYTVB_REQUIRE(!(halo_hi2 && !pb->time_scale_hi), "slab ends inside the volume: time_scale_hi (the scale's plane z = Nz) is required");
+    }
     if (axes_of(pb).z_on) {
         PYTVB_REQUIRE(!(pb->z_offset > 0 && !halo_lo2), "slab starts inside the volume: halo_lo2 (2 planes) is required");
         PYTVB_REQUIRE(!(pb->z_offset + pb->Nz < pb->Nz_global && !halo_hi2), "slab ends inside the volume: halo_hi2 (2 planes) is required");

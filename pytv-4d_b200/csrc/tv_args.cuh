@@ -1,0 +1,16 @@
+// Arguments of one pytvb_tv call, shared by tv.cu (entry point, two-sweep fallback) and tv_tile.cu (single-sweep kernel).
+#pragma once
+#include "host_common.cuh"
+
+namespace pytvb {
+
+template <typename T> struct TvArgs {
+    ImgView<T> X; ImgView<T> W; T* Wz0; T* G; T* norms; double* partial; Params<T> P; int z_lo, nz; cudaStream_t st;
+    long long* nblocks_out;
+    ImgView<T> TS;      // time-scale map with its one-plane z halos (tile kernel)
+};
+
+// tv_tile.cu
+template <typename T> int run_tv_tile(int vec, int scheme, bool z_on, bool t_on, const TvArgs<T>& a);
+
+}  // namespace pytvb

@@ -1,0 +1,46 @@
+// tv_<scheme>, single-sweep form: launch of the z-marching tile kernel (kernels_tile.cuh / tile_core.cuh).
+#include "host_common.cuh"
+#include "tv_path.cuh"
+#include "tv_args.cuh"
+
+using namespace pytvb;
+
+namespace {
+
+// ---- single-sweep tile kernel (kernels_tile.cuh): one launch, x read once, G written once
+template <typename T, int VEC, int SCHEME, bool Z, bool TT, int TSMODE>
+int launch_tile(const TvArgs<T>& a, const TileGeom& g, size_t smem) {
+    auto kern = tv_tile_kernel<T, VEC, SCHEME, Z, TT, PYTVB_TILE_R, TSMODE>;
+    static bool attr_set = false;      // per instantiation; the attribute is sticky for the function
+    if (!attr_set) {
+        PYTVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_LIMIT));
+        attr_set = true;
+    }
+    kern<<<(unsigned)g.nblocks, g.nthreads, smem, a.st>>>(a.X, a.TS, a.G, a.norms, a.partial, a.P, g);
+    count_launches(1);
+    PYTVB_CUDA(cudaGetLastError());
+    *a.nblocks_out = g.nblocks;
+    return PYTVB_OK;
+}
+template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchTvTile {
+    static int run(const TvArgs<T>& a) {
+        TileGeom g;
+        const bool mask = TT && a.P.mask_static;
+        PYTVB_REQUIRE((make_tile_geom<T, VEC, PYTVB_TILE_R>(g, a.P.Nz, a.P.M, a.P.Ni, a.P.Nj, TT, mask)), "internal: the tile kernel does not take this problem");
+        PYTVB_REQUIRE(g.nblocks > 0 && g.nblocks < 2147483647LL, "grid of %lld CTAs is out of range", g.nblocks);
+        const size_t smem = tile_smem_bytes<T>(g, mask);
+        if (TT && a.P.tscale) return launch_tile<T, VEC, SCHEME, Z, TT, TT ? 2 : 0>(a, g, smem);
+        if (mask) return launch_tile<T, VEC, SCHEME, Z, TT, TT ? 1 : 0>(a, g, smem);
+        return launch_tile<T, VEC, SCHEME, Z, TT, 0>(a, g, smem);
+    }
+};
+
+}  // namespace
+
+namespace pytvb {
+template <typename T> int run_tv_tile(int vec, int scheme, bool z_on, bool t_on, const TvArgs<T>& a) {
+    return dispatch<LaunchTvTile, T>(vec, scheme, z_on, t_on, a);
+}
+template int run_tv_tile<float>(int, int, bool, bool, const TvArgs<float>&);
+template int run_tv_tile<double>(int, int, bool, bool, const TvArgs<double>&);
+}  // namespace pytvb

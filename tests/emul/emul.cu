@@ -9,6 +9,7 @@
 #include "../../pytv-4d_b200/csrc/host_common.cuh"
 #include "../../pytv-4d_b200/csrc/strip_core.cuh"
 #include "gen1_quad.cuh"
+#include "../../pytv-4d_b200/csrc/tv_path.cuh"
 
 namespace pytvb {
 static char g_err[512];
@@ -242,6 +243,71 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct ETV2 {
     }
 };
 
+// Single-sweep tile kernel (kernels_tile.cuh), CTA by CTA; inside a CTA the phases between two barriers are run for all
+// threads one after the other, which is one valid execution of the kernel.
+static int g_tile_strips = 0, g_tile_Lz = 0;      // test overrides of the geometry (0 = what the library chooses)
+template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct ETile {
+    static int run(const EArgs<T>& a) {
+        constexpr int R = PYTVB_TILE_R;
+        TileGeom g;
+        const bool mask = TT && a.P.mask_static;
+        if (!make_tile_geom<T, VEC, R>(g, a.P.Nz, a.P.M, a.P.Ni, a.P.Nj, TT, mask)) return -20;
+        if (g_tile_strips > 0 && g_tile_strips < g.strips) {
+            g.strips = g_tile_strips; g.RPF = g.strips * R; g.TI = g.RPF - 2; g.rowsX = g.RPF + 2; g.slotX = g.rowsX * g.pitchX; g.slotW = g.RPF * g.WJ;
+            g.nthreads = 32 * g.FC * g.strips; g.nti = (a.P.Ni + g.TI - 1) / g.TI;
+            g.nblocks = (long long)g.nti * g.ntj * g.nfg * g.nzc;
+        }
+        if (g_tile_Lz > 0) { g.Lz = g_tile_Lz; g.nzc = (a.P.Nz + g.Lz - 1) / g.Lz; g.nblocks = (long long)g.nti * g.ntj * g.nfg * g.nzc; }
+        const int tsmode = (TT && a.P.tscale) ? 2 : (mask ? 1 : 0);
+        if (tsmode == 2) return run_mode<2>(a, g, mask);
+        if (tsmode == 1) return run_mode<1>(a, g, mask);
+        return run_mode<0>(a, g, mask);
+    }
+    template <int TSMODE> static int run_mode(const EArgs<T>& a, const TileGeom& g, bool mask) {
+        constexpr int R = PYTVB_TILE_R;
+        constexpr int TSM = TT ? TSMODE : 0;
+        std::vector<unsigned char> smem(tile_smem_bytes<T>(g, mask) + 16);
+        std::vector<TileThread<T, VEC, R>> st(g.nthreads);
+        double tv = 0;
+        for (long long b = 0; b < g.nblocks; ++b) {
+            std::fill(smem.begin(), smem.end(), (unsigned char)0xFF);      // NaN pattern: an unstaged element shows up in the results
+            const TileCtx<T> c = tile_ctx<T>(g, b, a.P.Nz, smem.data(), mask);
+            for (auto& s : st) memset(&s, 0, sizeof(s));
+            std::vector<TilePos> tps(g.nthreads);
+            for (int tid = 0; tid < g.nthreads; ++tid) tps[tid] = tile_pos<T, VEC, R>(c, g, a.P, tid);
+            auto all = [&](auto f) { for (int tid = 0; tid < g.nthreads; ++tid) f(tid); };
+            if (mask) all([&](int tid) { tile_stage_mask<T, VEC>(c, g, a.P, tid); });
+            all([&](int tid) { tile_stage_tables<T>(c, g, a.P, tid); });
+            if (Z) {
+                const int p0 = c.zc0 - 1, p1 = c.zc1;
+                all([&](int tid) { tile_stage_plane<T, VEC>(c, g, a.X, a.P, p0, tid); tile_stage_plane<T, VEC>(c, g, a.X, a.P, p0 + 1, tid); });
+                all([&](int tid) { tile_init_z<T, VEC, SCHEME, R>(st[tid], c, g, a.X, a.P, p0, tps[tid]); });
+                for (int p = p0; p <= p1; ++p) {
+                    // the staging of plane p+2 is asynchronous on the device: it may land at any time before the end of the step.
+                    // Emulate the two extremes on alternating steps: before the w-phase / after the G-phase.
+                    const bool early = (p & 1) != 0;
+                    if (early && p + 2 <= p1 + 1) all([&](int tid) { tile_stage_plane<T, VEC>(c, g, a.X, a.P, p + 2, tid); });
+                    all([&](int tid) { tile_phase_w<T, VEC, SCHEME, Z, TT, R, TSM>(st[tid], c, g, a.P, a.W, a.out, a.out2, p, tps[tid]); });
+                    if (p >= c.zc0 && p < c.zc1) all([&](int tid) { tile_phase_g<T, VEC, SCHEME, Z, TT, R, TSM>(st[tid], c, g, a.P, a.W, a.out, p, tps[tid]); });
+                    if (!early && p + 2 <= p1 + 1) all([&](int tid) { tile_stage_plane<T, VEC>(c, g, a.X, a.P, p + 2, tid); });
+                }
+            } else {
+                all([&](int tid) { tile_stage_plane<T, VEC>(c, g, a.X, a.P, c.zc0, tid); });
+                for (int p = c.zc0; p < c.zc1; ++p) {
+                    const bool early = (p & 1) != 0;
+                    if (early && p + 1 < c.zc1) all([&](int tid) { tile_stage_plane<T, VEC>(c, g, a.X, a.P, p + 1, tid); });
+                    all([&](int tid) { tile_phase_w<T, VEC, SCHEME, Z, TT, R, TSM>(st[tid], c, g, a.P, a.W, a.out, a.out2, p, tps[tid]); });
+                    all([&](int tid) { tile_phase_g<T, VEC, SCHEME, Z, TT, R, TSM>(st[tid], c, g, a.P, a.W, a.out, p, tps[tid]); });
+                    if (!early && p + 1 < c.zc1) all([&](int tid) { tile_stage_plane<T, VEC>(c, g, a.X, a.P, p + 1, tid); });
+                }
+            }
+            for (auto& s : st) tv += (double)s.tv;
+        }
+        *a.sum = tv;
+        return 0;
+    }
+};
+
 template <typename T> int vec_for(const pytvb_problem* pb, int force_scalar) {
     return (force_scalar || pb->Nj % VecOf<T>::value) ? 1 : VecOf<T>::value;
 }
@@ -261,6 +327,14 @@ int run(int op, const pytvb_problem* pb, const void* in, void* out, void* out2, 
         case 1: a.F = FieldView<T>{(const T*)in, (const T*)lo, (const T*)hi}; return dispatch<EDT, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
         case 7: a.X = ImgView<T>{(const T*)in, (const T*)lo, (const T*)hi, 1}; return dispatch<ED2, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
         case 8: a.F = FieldView<T>{(const T*)in, (const T*)lo, (const T*)hi}; return dispatch<EDT2, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
+        case 10:
+            if (tv_uses_tile(pb)) {   // tile kernel: in = x, out = G, out2 = norms | NULL; lo / hi = two halo planes each; a.W carries the time-scale view
+                a.X = ImgView<T>{(const T*)in, (const T*)lo, (const T*)hi, 2};
+                a.W = ImgView<T>{a.P.tscale, (const T*)pb->time_scale_lo, (const T*)pb->time_scale_hi, 1};
+                return dispatch<ETile, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
+            }
+            op = 9;   // the problems the library sends to the two-sweep fallback
+            // fall through
         case 2:
         case 9: {
             const bool has_lo = ax.z_on && pb->z_offset > 0, has_hi = ax.z_on && pb->z_offset + pb->Nz < pb->Nz_global;
@@ -414,4 +488,5 @@ extern "C" int pytvb_emulate_f16y(int op, const pytvb_problem* pb, const void* i
 }
 
 extern "C" void pytvb_emulate_set_rows(int r) { g_emul_rows = (r == 4) ? 4 : 8; }
+extern "C" void pytvb_emulate_set_tile(int strips, int Lz) { g_tile_strips = strips; g_tile_Lz = Lz; }
 extern "C" const char* pytvb_emulate_error(void) { return g_err; }

@@ -17,7 +17,7 @@ from pytv_b200 import _lib  # noqa: E402
 
 def build_emul(force=False):
     src = os.path.join(EMUL_DIR, "emul.cu")
-    deps = [src] + [os.path.join(ROOT, "pytv-4d_b200", "csrc", f) for f in ("core.cuh", "strip_core.cuh", "kernels.cuh", "kernels2.cuh", "host_common.cuh")] + [os.path.join(EMUL_DIR, "gen1_quad.cuh")]
+    deps = [src] + [os.path.join(ROOT, "pytv-4d_b200", "csrc", f) for f in ("core.cuh", "strip_core.cuh", "tile_core.cuh", "kernels.cuh", "kernels2.cuh", "kernels_tile.cuh", "host_common.cuh")] + [os.path.join(EMUL_DIR, "gen1_quad.cuh")]
     if not force and os.path.exists(EMUL_SO) and all(os.path.getmtime(EMUL_SO) >= os.path.getmtime(d) for d in deps):
         return EMUL_SO
     cmd = ["nvcc", "-O1", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "--extended-lambda", "-gencode",
@@ -26,7 +26,7 @@ def build_emul(force=False):
     return EMUL_SO
 
 
-GEN = 1   # 1: tests/emul/gen1_quad.cuh (retired generation-1 code), 2: strip_core.cuh = what the library runs (module-level switch used by the tests)
+GEN = 1   # 1: tests/emul/gen1_quad.cuh (retired generation-1 code), 2: strip_core.cuh, 3: strip_core.cuh with tv through the single-sweep tile kernel (tile_core.cuh) = what the library runs
 _h = None
 
 
@@ -44,6 +44,12 @@ def emul():
 def set_tv_rows(r):
     """Rows per thread of the emulated TV sweeps: 8 (what libpytv_b200.so runs) or 4."""
     emul().pytvb_emulate_set_rows(int(r))
+
+
+def set_tile(strips=0, Lz=0):
+    """Geometry overrides of the emulated tile kernel: strips per frame (smaller tiles -> more CTAs along i) and z-chunk length
+    (0 = what the library chooses)."""
+    emul().pytvb_emulate_set_tile(int(strips), int(Lz))
 
 
 def _ptr(a):
@@ -97,12 +103,16 @@ def D_T(p, scheme, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_r
 
 
 def tv(x, scheme, reg_z_over_reg=1.0, reg_time=0.0, mask_static=False, factor_reg_static=0.0, lo=None, hi=None, z_offset=0, Nz_global=None,
-       scalar=False, time_weight=None):
+       scalar=False, time_weight=None, time_scale_halos=None):
     x = np.ascontiguousarray(x)
     pb, keep = _problem(scheme, x.dtype, x.shape, reg_z_over_reg, reg_time, mask_static, factor_reg_static, z_offset, Nz_global, time_weight)
     G = np.full(x.shape, np.nan, dtype=x.dtype)
     norms = np.full(x.shape, np.nan, dtype=x.dtype)
-    val = _call(2 if GEN == 1 else 9, pb, x, G, out2=norms, lo=lo, hi=hi, scalar=scalar)
+    if time_scale_halos is not None:      # (plane z = -1, plane z = Nz) of the sqrt weight map, for slabs (tile kernel)
+        tlo, thi = (None if h is None else np.ascontiguousarray(np.sqrt(np.asarray(h, dtype=np.float64)).astype(x.dtype)) for h in time_scale_halos)
+        pb.time_scale_lo = tlo.ctypes.data if tlo is not None else None
+        pb.time_scale_hi = thi.ctypes.data if thi is not None else None
+    val = _call({1: 2, 2: 9, 3: 10}[GEN], pb, x, G, out2=norms, lo=lo, hi=hi, scalar=scalar)
     return val, G, norms
 
 
@@ -236,7 +246,7 @@ class EmulSlabOps:
         self._run(8, pb, p, out, lo=lo, hi=hi)
 
     def tv(self, pb, x, G, norms, d_tv, lo2, hi2):
-        d_tv[0] = self._run(9, pb, x, G, out2=norms, lo=lo2, hi=hi2)
+        d_tv[0] = self._run(10, pb, x, G, out2=norms, lo=lo2, hi=hi2)      # the tile kernel (or the fallback the library would pick)
 
     def l21(self, pb, D, Nd, d_sum):
         import torch

@@ -26,14 +26,14 @@ def test_header_symbols_are_exported_and_bound():
     for n in names:
         assert hasattr(handle, n), "%s declared in the header but not exported" % n
     assert sorted(_lib._PROTOTYPES) == names, "ctypes prototypes and header drifted apart"
-    assert _lib.lib().pytvb_version() == 100
+    assert _lib.lib().pytvb_version() == 101
 
 
 def test_problem_struct_layout_matches_header():
-    # 2 x int32, 6 x int64, 3 x double, 2 pointers, no padding surprises
-    assert ctypes.sizeof(_lib.Problem) == 8 + 6 * 8 + 3 * 8 + 2 * 8
+    # 2 x int32, 6 x int64, 3 x double, 4 pointers, no padding surprises
+    assert ctypes.sizeof(_lib.Problem) == 8 + 6 * 8 + 3 * 8 + 4 * 8
     assert _lib.Problem.Nz.offset == 8 and _lib.Problem.reg_z_over_reg.offset == 56 and _lib.Problem.mask_static.offset == 80
-    assert _lib.Problem.time_scale.offset == 88
+    assert _lib.Problem.time_scale.offset == 88 and _lib.Problem.time_scale_lo.offset == 96 and _lib.Problem.time_scale_hi.offset == 104
 
 
 @pytest.mark.parametrize("scheme,Nz,M,rz,rt,expect", [
@@ -76,7 +76,9 @@ def test_workspace_sizes():
     r = lib.pytvb_reduce_workspace_bytes(ctypes.byref(pb))
     t = lib.pytvb_tv_workspace_bytes(ctypes.byref(pb))
     assert r >= 8 * (256 + 20 * 4 * 100 * 100 // 256)
-    assert t >= 22 * 4 * 100 * 100 * 4
+    assert 0 < t <= 4096                      # the single-sweep kernel needs no inverse-norm field
+    many = _lib.make_problem("hybrid", _lib.F32, (3, 20, 16, 16), reg_time=1.0)     # 20 coupled frames: the two-sweep fallback
+    assert lib.pytvb_tv_workspace_bytes(ctypes.byref(many)) >= 5 * 20 * 16 * 16 * 4
 
 
 def test_partition_z():

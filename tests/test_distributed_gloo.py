@@ -155,3 +155,61 @@ def test_sharded_operators_and_tv_equal_whole_volume(tmp_path, scheme, world, Nz
     np.testing.assert_array_equal(cat("xm"), xm)
     np.testing.assert_allclose(cat("Gm"), Gm_o, atol=1e-12)
     assert parts[0]["scal"][2] == pytest.approx(tvm_o, rel=1e-13)
+
+
+def _weighted_worker(rank, world, port, scheme, Nz, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import emul_helper as em
+    import pytv_b200
+    from pytv_b200.sharded import ShardedTV
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rs = np.random.RandomState(29)
+        M, N = 3, 8
+        x = rs.rand(Nz, M, N, N)
+        W = rs.rand(Nz, M, N, N) * 3
+        ms = rs.rand(1, 1, N, N) > 0.5
+        off, cnt = pytv_b200.partition_z(Nz, world)[rank]
+        sh = ShardedTV(scheme, reg_z_over_reg=0.7, reg_time=0.3, mask_static=ms, factor_reg_static=2.0, ops=em.EmulSlabOps())
+        xs = torch.as_tensor(x[off:off + cnt].copy())
+        Ws = torch.as_tensor(W[off:off + cnt].copy())
+        Ds = sh.D(xs, time_weight=Ws)
+        p = rs.randn(Nz, Ds.shape[1], M, N, N)
+        DTs = sh.D_T(torch.as_tensor(p[off:off + cnt].copy()), time_weight=Ws)
+        tv, G, norms = sh.tv(xs.clone(), return_grad_norms=True, time_weight=Ws)
+        tv0, G0 = sh.tv(xs.clone())
+        np.savez(os.path.join(out_dir, "w%d.npz" % rank), D=Ds.numpy(), DT=DTs.numpy(), G=G.numpy(), norms=norms.numpy(), G0=G0.numpy(), scal=np.array([tv, tv0]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("scheme,world,Nz", [("hybrid", 2, 14), ("central", 2, 13), ("upwind", 3, 20)])
+def test_sharded_interior_split_and_weight_map(tmp_path, scheme, world, Nz):
+    """Slabs of >= 6 planes: the interior planes are computed before the halos arrive, the two boundary planes on each side
+    after (ShardedTV's overlapped schedule); with a (Nz, M, N, N) weight map of the time regularisation, whose boundary
+    planes travel with the image planes (pytvb_problem.time_scale_lo / _hi)."""
+    from oracle import tv_oracle as orc
+    mp.spawn(_weighted_worker, args=(world, _free_port(), scheme, Nz, str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(tmp_path / ("w%d.npz" % r)) for r in range(world)]
+    cat = lambda k: np.concatenate([p[k] for p in parts], axis=0)
+    rs = np.random.RandomState(29)
+    M, N = 3, 8
+    x = rs.rand(Nz, M, N, N)
+    W = rs.rand(Nz, M, N, N) * 3
+    ms = rs.rand(1, 1, N, N) > 0.5
+    kw = dict(reg_z_over_reg=0.7, reg_time=0.3, mask_static=ms, factor_reg_static=2.0)
+    D_o = orc.D(x, scheme, time_weight=W, **kw)
+    p = rs.randn(*D_o.shape)
+    np.testing.assert_allclose(cat("D"), D_o, atol=1e-14)
+    np.testing.assert_allclose(cat("DT"), orc.D_T(p, scheme, time_weight=W, **kw), atol=1e-13)
+    tv_o, G_o, n_o = orc.tv(x.copy(), scheme, return_grad_norms=True, time_weight=W, **kw)
+    np.testing.assert_allclose(cat("G"), G_o, atol=1e-12)
+    np.testing.assert_allclose(cat("norms"), n_o, atol=1e-13)
+    tv0_o, G0_o = orc.tv(x.copy(), scheme, **kw)
+    np.testing.assert_allclose(cat("G0"), G0_o, atol=1e-12)
+    for part in parts:
+        assert part["scal"][0] == pytest.approx(tv_o, rel=1e-13) and part["scal"][1] == pytest.approx(tv0_o, rel=1e-13)

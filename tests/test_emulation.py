@@ -1,5 +1,5 @@
-"""The per-quad CUDA code (pytv-4d_b200/csrc/tv_core.cuh), executed on the host quad by quad, against the
-oracle and the reference goldens.  This pins the index / boundary / halo / weight logic of the kernels
+"""The per-thread CUDA code (pytv-4d_b200/csrc/strip_core.cuh, tile_core.cuh; and the retired generation-1 code kept under
+tests/emul), executed on the host, against the oracle and the reference goldens.  This pins the index / boundary / halo / weight logic of the kernels
 without a GPU; the -m gpu tests then check the same functions through the real launches."""
 import numpy as np
 import pytest
@@ -11,16 +11,19 @@ from oracle import tv_oracle as orc
 SCHEMES = cases.SCHEMES
 
 
-@pytest.fixture(params=[(1, 8), (2, 8), (2, 4)], ids=["gen1", "gen2", "gen2-r4"])
+@pytest.fixture(params=[(1, 8, 0, 0), (2, 8, 0, 0), (2, 4, 0, 0), (3, 8, 0, 0), (3, 8, 1, 4)], ids=["gen1", "gen2", "gen2-r4", "tile", "tile-small"])
 def gen(request):
-    """Both kernel generations (tv_core.cuh quad code, strip_core.cuh strip code); the strip code's TV sweeps with 8 rows per
-    thread (what the library runs) and with 4 (other strip / image-height alignments)."""
+    """The retired generation-1 quad code; the strip code (operators, CP passes, the two-sweep tv fallback with 8 and 4 rows per
+    thread); and the strip code with tv through the single-sweep tile kernel - what the library runs - with the geometry the
+    library chooses and with the smallest tiles and 4-plane z chunks (many CTAs, every seam exercised)."""
     old = em.GEN
-    em.GEN, rows = request.param
+    em.GEN, rows, strips, Lz = request.param
     em.set_tv_rows(rows)
+    em.set_tile(strips, Lz)
     yield em.GEN
     em.GEN = old
     em.set_tv_rows(8)
+    em.set_tile(0, 0)
 
 
 def _tol(dtype):
@@ -353,11 +356,35 @@ def test_time_weight_map(scheme, shape, scalar):
         np.testing.assert_allclose(em.D(x, scheme, scalar=scalar, **kw), D_o, atol=1e-14)
         p = rs.randn(*D_o.shape)
         np.testing.assert_allclose(em.D_T(p, scheme, scalar=scalar, **kw), orc.D_T(p, scheme, **kw), atol=1e-13)
-        tv, G, n = em.tv(x, scheme, scalar=scalar, **kw)
         tv_o, G_o, n_o = orc.tv(x.copy(), scheme, return_grad_norms=True, **kw)
-        assert tv == pytest.approx(tv_o, rel=1e-13)
-        np.testing.assert_allclose(G, G_o, atol=1e-12)
-        np.testing.assert_allclose(n, n_o, atol=1e-13)
+        for g_, strips, Lz in ((2, 0, 0), (3, 0, 0), (3, 1, 4)):          # two-sweep fallback, tile kernel, tile kernel with small tiles
+            em.GEN = g_
+            em.set_tile(strips, Lz)
+            tv, G, n = em.tv(x, scheme, scalar=scalar, **kw)
+            assert tv == pytest.approx(tv_o, rel=1e-13)
+            np.testing.assert_allclose(G, G_o, atol=1e-12)
+            np.testing.assert_allclose(n, n_o, atol=1e-13)
+        # slabs with z halos (tile kernel): the weight map travels with one halo plane per side (pytvb_problem.time_scale_lo / _hi)
+        if Nz >= 3 and not (scheme == "central" and M == 2):
+            em.GEN = 3
+            tv_sum = 0.0
+            for a, b in ((0, 1), (1, Nz)):
+                lo2 = np.full((2, M, Ni, Nj), np.nan)
+                hi2 = np.full((2, M, Ni, Nj), np.nan)
+                for k in (1, 2):
+                    if a - k >= 0:
+                        lo2[2 - k] = x[a - k]
+                    if b + k - 1 < Nz:
+                        hi2[k - 1] = x[b + k - 1]
+                kws = dict(kw, time_weight=W[a:b])
+                tvs, Gs, ns = em.tv(np.ascontiguousarray(x[a:b]), scheme, scalar=scalar, lo=lo2 if a > 0 else None, hi=hi2 if b < Nz else None, z_offset=a,
+                                    Nz_global=Nz, time_scale_halos=(W[a - 1] if a > 0 else None, W[b] if b < Nz else None), **kws)
+                np.testing.assert_allclose(Gs, G_o[a:b], atol=1e-12)
+                np.testing.assert_allclose(ns, n_o[a:b], atol=1e-13)
+                tv_sum += tvs
+            assert tv_sum == pytest.approx(tv_o, rel=1e-13)
+        em.GEN = 2
+        em.set_tile(0, 0)
         Nd = D_o.shape[1]
         y = 0.2 * rs.randn(Nz, Nd, M, Ni, Nj)
         xx = x + 0.1 * rs.randn(*shape)

@@ -20,8 +20,9 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, scheme, out_dir, mode, variant="rof"):
+def _worker(rank, world, port, scheme, out_dir, mode, variant="rof", weighted=False, sync="auto"):
     os.environ["PYTVB_OVERLAP"] = "1" if mode == "overlap" else "0"
+    os.environ["PYTVB_P2P_SYNC"] = sync
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     import pytv_b200
@@ -33,8 +34,9 @@ def _worker(rank, world, port, scheme, out_dir, mode, variant="rof"):
         g = torch.Generator().manual_seed(3)
         x0 = torch.rand(12, 3, 64, 64, generator=g)
         off, cnt = pytv_b200.partition_z(12, world)[rank]
+        tw = (torch.rand(12, 3, 64, 64, generator=g) * 3)[off:off + cnt].cuda() if weighted else None
         s = pytv_b200.CPSolver(x0[off:off + cnt].cuda(), lam=0.1, scheme=scheme, reg_time=0.25, distributed=True,
-                                comm=mode if mode in ("p2p", "auto") else "nccl", variant=variant)
+                                comm=mode if mode in ("p2p", "auto") else "nccl", variant=variant, time_weight=tw)
         if mode != "auto":        # auto: peer memory where the box offers it, NCCL otherwise - the result is the same
             assert (s._peer is not None) == (mode == "p2p")
         energies = []
@@ -78,7 +80,7 @@ def test_two_gpu_sharded_cp_equals_single_gpu(tmp_path, scheme, mode):
     assert abs(e[7] - energies[7]) <= 1e-9 * abs(energies[5])
 
 
-def _sharded_worker(rank, world, port, scheme, out_dir):
+def _sharded_worker(rank, world, port, scheme, out_dir, comm="nccl", Nz=10, weighted=False):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     import pytv_b200
@@ -89,37 +91,48 @@ def _sharded_worker(rank, world, port, scheme, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         g = torch.Generator().manual_seed(5)
-        x = torch.rand(10, 3, 64, 64, generator=g)
+        x = torch.rand(Nz, 3, 64, 64, generator=g)
         ms = torch.rand(1, 1, 64, 64, generator=g) > 0.5
-        off, cnt = pytv_b200.partition_z(10, world)[rank]
-        sh = ShardedTV(scheme, reg_z_over_reg=0.7, reg_time=0.3, mask_static=ms, factor_reg_static=2.0)
+        W = torch.rand(Nz, 3, 64, 64, generator=g) * 3
+        off, cnt = pytv_b200.partition_z(Nz, world)[rank]
+        sh = ShardedTV(scheme, reg_z_over_reg=0.7, reg_time=0.3, mask_static=ms, factor_reg_static=2.0, comm=comm)
         xs = x[off:off + cnt].cuda()
-        Ds = sh.D(xs)
-        p = torch.randn(10, Ds.shape[1], 3, 64, 64, generator=g)
-        DTs = sh.D_T(p[off:off + cnt].cuda())
-        l21 = sh.l21(Ds)
-        tv, G, norms = sh.tv(xs, return_grad_norms=True)
+        tw = W[off:off + cnt].cuda() if weighted else None
+        for rep in range(3):      # repeated calls: the peer buffers alternate, a rank may run one call ahead of its neighbour
+            Ds = sh.D(xs, time_weight=tw)
+            p = torch.randn(Nz, Ds.shape[1], 3, 64, 64, generator=torch.Generator().manual_seed(6))
+            DTs = sh.D_T(p[off:off + cnt].cuda(), time_weight=tw)
+            l21 = sh.l21(Ds)
+            tv, G, norms = sh.tv(xs, return_grad_norms=True, time_weight=tw)
+        assert sh.transport == ("p2p" if comm == "p2p" else sh.transport)
         np.savez(os.path.join(out_dir, "s%d.npz" % rank), D=Ds.cpu().numpy(), DT=DTs.cpu().numpy(), G=G.cpu().numpy(), norms=norms.cpu().numpy(),
                  scal=np.array([l21, tv]))
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("comm,Nz,weighted", [("nccl", 10, False), ("p2p", 10, False), ("p2p", 17, True), ("nccl", 17, True)],
+                         ids=["nccl", "p2p", "p2p-interior-weighted", "nccl-interior-weighted"])
 @pytest.mark.parametrize("scheme", ["hybrid", "central", "downwind"])
-def test_two_gpu_sharded_operators_equal_single_gpu(tmp_path, scheme):
-    """ShardedTV over NCCL on two GPUs: bitwise the single-GPU drop-in results on the whole volume."""
+def test_two_gpu_sharded_operators_equal_single_gpu(tmp_path, scheme, comm, Nz, weighted):
+    """ShardedTV on two GPUs - halo planes by NCCL send/recv or stored straight into the neighbour's peer-mapped buffers,
+    slabs of 5 planes (whole-slab calls) and of 8-9 planes (interior first, boundary planes after the halos landed), with and
+    without a weight map of the time regularisation: bitwise the single-GPU drop-in results on the whole volume."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import pytv_b200 as pytv
-    mp.spawn(_sharded_worker, args=(2, _free_port(), scheme, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_sharded_worker, args=(2, _free_port(), scheme, str(tmp_path), comm, Nz, weighted), nprocs=2, join=True)
     parts = [np.load(tmp_path / ("s%d.npz" % r)) for r in range(2)]
     cat = lambda k: np.concatenate([q[k] for q in parts], axis=0)
     g = torch.Generator().manual_seed(5)
-    x = torch.rand(10, 3, 64, 64, generator=g)
+    x = torch.rand(Nz, 3, 64, 64, generator=g)
     ms = torch.rand(1, 1, 64, 64, generator=g) > 0.5
+    W = torch.rand(Nz, 3, 64, 64, generator=g) * 3
     kw = dict(reg_z_over_reg=0.7, reg_time=0.3, mask_static=ms, factor_reg_static=2.0)
+    if weighted:
+        kw["time_weight"] = W.cuda()
     D1 = getattr(pytv.tv_operators_GPU, "D_" + scheme)(x.cuda(), **kw)
-    p = torch.randn(10, D1.shape[1], 3, 64, 64, generator=g)
+    p = torch.randn(Nz, D1.shape[1], 3, 64, 64, generator=torch.Generator().manual_seed(6))
     DT1 = getattr(pytv.tv_operators_GPU, "D_T_" + scheme)(p.cuda(), **kw)
     tv1, G1, n1 = getattr(pytv.tv_GPU, "tv_" + scheme)(x.cuda(), return_pytorch_tensor=True, return_grad_norms=True, **kw)
     np.testing.assert_array_equal(cat("D"), D1.cpu().numpy())
@@ -146,3 +159,26 @@ def test_two_gpu_peer_halo_push_readme_variant(tmp_path):
         energies.append(s.energy())
     np.testing.assert_array_equal(x, s.result())
     np.testing.assert_allclose(np.load(tmp_path / "e.npy"), energies, rtol=1e-12)
+
+
+@pytest.mark.parametrize("sync", ["auto", "barrier"])
+def test_two_gpu_peer_halo_push_with_weight_map(tmp_path, sync):
+    """Peer-memory halo push together with a (Nz, M, N, N) weight map of the time regularisation (the combination round 1
+    refused), with the neighbour-only handshake and with the group-wide barrier as the fence between passes."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import pytv_b200
+    mp.spawn(_worker, args=(2, _free_port(), "hybrid", str(tmp_path), "p2p", "rof", True, sync), nprocs=2, join=True)
+    x = np.concatenate([np.load(tmp_path / ("x_%d.npy" % r)) for r in range(2)], axis=0)
+    g = torch.Generator().manual_seed(3)
+    x0 = torch.rand(12, 3, 64, 64, generator=g)
+    tw = torch.rand(12, 3, 64, 64, generator=g) * 3
+    s = pytv_b200.CPSolver(x0.cuda(), lam=0.1, scheme="hybrid", variant="rof", reg_time=0.25, time_weight=tw.cuda())
+    energies = []
+    for _ in range(5):
+        s.step()
+        energies.append(s.energy())
+    energies.extend(s.gap())
+    s.step(2)
+    np.testing.assert_array_equal(x, s.result())
+    np.testing.assert_allclose(np.load(tmp_path / "e.npy")[:5], energies[:5], rtol=1e-12)

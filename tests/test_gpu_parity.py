@@ -75,11 +75,18 @@ def test_small_goldens_float32(case, golden_small):
     assert float(tv) == pytest.approx(float(golden_small[key + "/tv"]), rel=1e-5)
     gn = golden_small[key + "/norms"]
     assert np.array_equal(np.isinf(norms), np.isinf(gn))
-    # sub-gradient: 1e-5 absolute wherever the neighbourhood norms are not tiny (G divides by them)
-    _, G32 = orc.tv(x.copy(), scheme, **kw)
-    np.testing.assert_allclose(G, G32, rtol=0, atol=2e-4)
-    if np.all(gn[np.isfinite(gn)] > 0.05):
-        np.testing.assert_allclose(G, golden_small[key + "/G"], rtol=0, atol=1e-5)
+    # sub-gradient: 1e-5 absolute (north star), or - where D/|D| is ill-conditioned because the norms are tiny - 3 x the
+    # rounding floor of the reference formula itself evaluated in float32 (numpy).  Measured on the B200 (profiles/
+    # r02a_ref_fp32.json): this library sits AT that floor (7e-7 .. 1.6e-6 on the README volume), the reference's own
+    # float32 GPU path is at 5e-3 .. 5e-1 (its conv3d calls run in TF32).
+    _assert_G_float32(G, golden_small[key + "/G"], x, scheme, kw)
+
+
+def _assert_G_float32(G, G64, x32, scheme, kw):
+    _, G32 = orc.tv(x32.copy(), scheme, **kw)
+    floor = float(np.abs(G32.astype(np.float64) - G64).max())
+    err = float(np.abs(G.astype(np.float64) - G64).max())
+    assert err <= max(1e-5, 3.0 * floor), (err, floor)
 
 
 # ------------------------------------------------------------------ published known answers
@@ -113,8 +120,11 @@ def test_readme_volume_known_answers(scheme, golden_kat):
     tv32, G32 = tv_(scheme)(img32.copy())
     assert G32.dtype == np.float32
     assert float(tv32) == pytest.approx(g["default"]["tv"], rel=1e-5)
-    err = np.abs(G32 - G_o)
-    assert err.max() < 1e-4 and np.mean(err < 1e-5) > 0.999, (err.max(), np.mean(err < 1e-5))
+    # same float32 input through the float64 oracle: 1e-5 absolute, no escape hatch (measured: 4e-7 central .. 1.6e-6 hybrid)
+    _, G_o32in = orc.tv(img32.astype(np.float64), scheme)
+    assert float(np.abs(G32 - G_o32in).max()) <= 1e-5
+    # against the float64 INPUT the rounding of the image itself enters (amplified where |Dx| is small): README.md:85's check
+    assert np.mean(np.abs(G32 - G_o) < 1e-5) > 0.999
 
 
 def test_readme_published_value():
@@ -385,7 +395,7 @@ def test_time_weight_map(scheme, golden_small):
 @pytest.mark.parametrize("shape", [(3, 2, 5, 8), (2, 3, 6, 4), (1, 1, 7, 12), (5, 1, 4, 8), (1, 4, 3, 4), (2, 2, 1, 4), (3, 3, 2, 8), (4, 2, 33, 260)],
                          ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("scheme", SCHEMES)
-def test_cp_single_iteration_all_shapes(scheme, shape, gen):
+def test_cp_single_iteration_all_shapes(scheme, shape):
     """One iteration from a random state (y non-zero also at the structurally-zero positions the adjoint must
     ignore) on small, degenerate and multi-CTA shapes; weights and mask_static on; float64 against the oracle."""
     lib = _lib.lib()
@@ -418,7 +428,7 @@ def test_cp_single_iteration_all_shapes(scheme, shape, gen):
 
 @pytest.mark.parametrize("scheme", SCHEMES)
 @pytest.mark.parametrize("dtype", [np.float64, np.float32], ids=["f64", "f32"])
-def test_cp_small4d_golden(scheme, dtype, golden_kat, gen):
+def test_cp_small4d_golden(scheme, dtype, golden_kat):
     g = golden_kat["cp_small4d"][scheme]
     x0 = cases.cp_volume().astype(dtype)
     kw = dict(reg_z_over_reg=0.5, reg_time=2 ** -5, mask_static=cases.cp_mask_static(), factor_reg_static=4.0)
@@ -702,7 +712,8 @@ def test_host_entry_points():
                                  norms.ctypes.data_as(ctypes.c_void_p), ctypes.byref(tv)))
     tv_o, G_o = orc.tv(x.copy(), "hybrid", reg_z_over_reg=0.5, reg_time=0.25, mask_static=ms.reshape(1, 1, 16, 16).astype(bool), factor_reg_static=4.0)
     assert tv.value == pytest.approx(float(tv_o), rel=1e-5)
-    np.testing.assert_allclose(G, G_o, atol=2e-4)
+    _, G64 = orc.tv(x.astype(np.float64), "hybrid", reg_z_over_reg=0.5, reg_time=0.25, mask_static=ms.reshape(1, 1, 16, 16).astype(bool), factor_reg_static=4.0)
+    _assert_G_float32(G, G64, x, "hybrid", dict(reg_z_over_reg=0.5, reg_time=0.25, mask_static=ms.reshape(1, 1, 16, 16).astype(bool), factor_reg_static=4.0))
     # streaming CP solver on host buffers == CPSolver on device buffers
     handle = ctypes.c_void_p()
     _lib.check(lib.pytvb_cp_create(ctypes.byref(pb), 0.2, 0.5, 1.0 / 17.0, 1.0, ctypes.byref(handle)))
