@@ -16,3 +16,4 @@ from . import tv_GPU          # noqa: F401
 from . import cp              # noqa: F401
 from . import sharded         # noqa: F401
 from .cp import CPSolver, TVProx, cp_denoise, denoise_tv_chambolle, gd_denoise, partition_z  # noqa: F401
+from .tv_GPU import TVPlan  # noqa: F401

@@ -790,33 +790,58 @@ def denoise_tv_chambolle(image, weight=0.1, eps=2e-4, max_num_iter=200, channel_
     return out if was_tensor else out.cpu().numpy()
 
 
-def gd_denoise(x0, lam, n_iter, step, scheme="hybrid", return_pytorch_tensor=False, return_losses=False, **weights):
+def gd_denoise(x0, lam, n_iter, step, scheme="hybrid", return_pytorch_tensor=False, return_losses=False, graph=None, reg_z_over_reg=1.0,
+               reg_time=0.0, mask_static=False, factor_reg_static=0, time_weight=None):
     """The README's sub-gradient descent loop (README.md:107-124) with the state resident on the device:
         tv, G = tv_<scheme>(x);  x <- x - step ((x - x0) + lam G);  loss = 0.5 |x - x0|^2 + lam tv
-    `weights`: reg_z_over_reg, reg_time, mask_static, factor_reg_static.  Returns x (and the loss history, one entry per
-    iteration, read back once at the end)."""
+    Two launches per iteration: the single-sweep tv kernel, and one fused kernel for the update and the data term of the
+    loss (`pytvb_gd_update`); the partial-sum reductions ride along.  The whole loop is captured into one CUDA graph and
+    replayed (graph=None: when the volume is small enough for launch overhead to matter, < 2^22 voxels), so a small image
+    costs a few microseconds per iteration instead of a host round trip per launch.  Returns x (and the loss history,
+    one entry per iteration, read back once at the end)."""
     x0d, was_tensor = _dev.to_device(x0)
+    if x0d.data_ptr() == (x0.data_ptr() if isinstance(x0, torch.Tensor) else 0):
+        x0d = x0d.clone()
     shape = _dev.image_shape(x0d)
     lib = _lib.lib()
-    ms = _dev.mask_static_to_device(weights.get("mask_static", False), shape[2], shape[3])
-    pb = _dev.problem(scheme, x0d, shape, weights.get("reg_z_over_reg", 1.0), weights.get("reg_time", 0.0), weights.get("factor_reg_static", 0), ms)
+    n_iter = int(n_iter)
+    ms = _dev.mask_static_to_device(mask_static, shape[2], shape[3])
+    ts = _dev.time_scale_to_device(time_weight, shape, x0d)
+    pb = _dev.problem(scheme, x0d, shape, reg_z_over_reg, reg_time, factor_reg_static, ms, ts=ts)
     x = x0d.clone()
     G = torch.empty_like(x)
     ws_r = _dev.reduce_workspace(pb, x.device)
     ws_t = torch.empty(lib.pytvb_tv_workspace_bytes(ctypes.byref(pb)), dtype=torch.uint8, device=x.device)
-    tvs = torch.zeros(int(n_iter), dtype=torch.float64, device=x.device)
-    fids = torch.zeros(int(n_iter), dtype=torch.float64, device=x.device)
-    st = _dev.stream_ptr()
-    for it in range(int(n_iter)):
+    tvs = torch.zeros(max(n_iter, 1), dtype=torch.float64, device=x.device)
+    fids = torch.zeros(max(n_iter, 1), dtype=torch.float64, device=x.device)
+
+    def iteration(it):
+        st = _dev.stream_ptr()
         _lib.check(lib.pytvb_tv(ctypes.byref(pb), _dev.ptr(x), _dev.ptr(G), None, _dev.ptr(tvs[it:it + 1]), None, None, _dev.ptr(ws_r), _dev.ptr(ws_t), st))
-        # x += -step * ((x - x0) + lam * G)
-        G.mul_(lam).add_(x).sub_(x0d)
-        x.add_(G, alpha=-float(step))
-        if return_losses:
-            fids[it] = torch.sum((x - x0d).double() ** 2)
+        _lib.check(lib.pytvb_gd_update(ctypes.byref(pb), _dev.ptr(x), _dev.ptr(x0d), _dev.ptr(G), float(step), float(lam),
+                                       _dev.ptr(fids[it:it + 1]) if return_losses else None, _dev.ptr(ws_r), st))
+
+    if graph is None:
+        graph = x.numel() < (1 << 22) and n_iter >= 8
+    if graph and n_iter > 0:
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            iteration(0)                      # warm-up outside the capture (lazy module loading, function attributes)
+        torch.cuda.current_stream().wait_stream(side)
+        x.copy_(x0d)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for it in range(n_iter):
+                iteration(it)
+        g.replay()
+    else:
+        for it in range(n_iter):
+            iteration(it)
     out = x if (return_pytorch_tensor or was_tensor) else x.cpu().numpy()
     if return_losses:
-        return out, (0.5 * fids + float(lam) * tvs).cpu().numpy()
+        return out, (0.5 * fids[:n_iter] + float(lam) * tvs[:n_iter]).cpu().numpy()
     return out
 
 

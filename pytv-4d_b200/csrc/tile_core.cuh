@@ -24,6 +24,75 @@
 
 namespace pytvb {
 
+// ---- element-wise arithmetic on the VEC values of a quad.  The kernel is instruction-issue bound (profiles/r02d_*: 63 %
+// issue utilisation, FP32 40 % of the executed instructions), and sm_100 has packed FP32 instructions - FADD2 / FMUL2 / FFMA2
+// (PTX add/mul/fma.rn.f32x2) - that do two IEEE operations in one issue slot (measured: the same FMA rate as the scalar form,
+// half the issue slots, profiles/r02a_ffma2.txt).  On the device, for float quads, every operation below is two packed
+// instructions instead of four scalar ones; the values are the same as those of the scalar code with the same fusion.  On the
+// host (tests/emul) and for double the plain loops run.
+template <typename T, int VEC>
+struct VOp {
+    static constexpr bool PACKED = false;
+    static PYTVB_HD void sub(T* d, const T* a, const T* b) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) d[e] = a[e] - b[e];
+    }
+    static PYTVB_HD void add(T* d, const T* a, const T* b) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) d[e] = a[e] + b[e];
+    }
+    static PYTVB_HD void mul(T* d, const T* a, const T* b) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) d[e] = a[e] * b[e];
+    }
+    static PYTVB_HD void fma(T* d, const T* a, const T* b, const T* c) {     // d = a * b + c (fused where the target fuses)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) d[e] = a[e] * b[e] + c[e];
+    }
+    static PYTVB_HD void muls(T* d, const T* a, T k) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) d[e] = a[e] * k;
+    }
+    static PYTVB_HD void fmas(T* d, const T* a, T k, const T* c) {           // d = a * k + c
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) d[e] = a[e] * k + c[e];
+    }
+};
+#if defined(__CUDA_ARCH__)
+#define PYTVB_F2_BIN(NAME, INS)                                                                                        \
+    static __device__ __forceinline__ void NAME(float* d, const float* a, const float* b) {                           \
+        _Pragma("unroll") for (int e = 0; e < 4; e += 2)                                                               \
+            asm("{ .reg .b64 ra, rb, rd;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n " INS " rd, ra, rb;\n mov.b64 {%0, %1}, rd; }" \
+                : "=f"(d[e]), "=f"(d[e + 1]) : "f"(a[e]), "f"(a[e + 1]), "f"(b[e]), "f"(b[e + 1]));                    \
+    }
+template <>
+struct VOp<float, 4> {
+    static constexpr bool PACKED = true;
+    PYTVB_F2_BIN(sub, "sub.rn.f32x2")
+    PYTVB_F2_BIN(add, "add.rn.f32x2")
+    PYTVB_F2_BIN(mul, "mul.rn.f32x2")
+    static __device__ __forceinline__ void fma(float* d, const float* a, const float* b, const float* c) {
+#pragma unroll
+        for (int e = 0; e < 4; e += 2)
+            asm("{ .reg .b64 ra, rb, rc, rd;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n mov.b64 rc, {%6, %7};\n fma.rn.f32x2 rd, ra, rb, rc;\n mov.b64 {%0, %1}, rd; }"
+                : "=f"(d[e]), "=f"(d[e + 1]) : "f"(a[e]), "f"(a[e + 1]), "f"(b[e]), "f"(b[e + 1]), "f"(c[e]), "f"(c[e + 1]));
+    }
+    static __device__ __forceinline__ void muls(float* d, const float* a, float k) {
+#pragma unroll
+        for (int e = 0; e < 4; e += 2)
+            asm("{ .reg .b64 ra, rb, rd;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %4};\n mul.rn.f32x2 rd, ra, rb;\n mov.b64 {%0, %1}, rd; }"
+                : "=f"(d[e]), "=f"(d[e + 1]) : "f"(a[e]), "f"(a[e + 1]), "f"(k));
+    }
+    static __device__ __forceinline__ void fmas(float* d, const float* a, float k, const float* c) {
+#pragma unroll
+        for (int e = 0; e < 4; e += 2)
+            asm("{ .reg .b64 ra, rb, rc, rd;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %4};\n mov.b64 rc, {%5, %6};\n fma.rn.f32x2 rd, ra, rb, rc;\n mov.b64 {%0, %1}, rd; }"
+                : "=f"(d[e]), "=f"(d[e + 1]) : "f"(a[e]), "f"(a[e + 1]), "f"(k), "f"(c[e]), "f"(c[e + 1]));
+    }
+};
+#undef PYTVB_F2_BIN
+#endif
+
 // Geometry of one launch (host-computed, warp-uniform).
 struct TileGeom {
     int strips;        // R-row strips per frame handled by one CTA
@@ -33,6 +102,7 @@ struct TileGeom {
     int WJ;            // work columns = 32 * VEC (tile columns -VEC .. TJ+VEC-1)
     int pitchX, rowsX; // x window: rows -2 .. TI+1, columns -VEC-1 .. TJ+VEC  (pitch = WJ + 2 VEC)
     int slotX, slotW;  // elements of one (plane, frame) x window / w window
+    int xslot;         // elements from one plane slot of the x window to the next (FC * slotX rounded up to 128 bytes: TMA destination alignment)
     int nti, ntj, nfg, nzc, Lz;   // tiles along i, j; frame groups; z chunks and their length
     int nthreads;
     long long nblocks;
@@ -56,6 +126,7 @@ struct TileCtx {
     int* rowd;         // [FC * rowsX] staging table: element offset of window row r inside a slot group (frame, row)
     int i0, j0, t0;    // global row / column of tile (0, 0); first frame
     int zc0, zc1;      // output planes [zc0, zc1), slab-local
+    bool fix;          // the x window reaches outside the image: zero-filled (TMA) windows need tile_fixup_plane
 };
 
 // Per-thread state carried from one z step to the next.
@@ -119,7 +190,7 @@ template <typename T, int VEC>
 PYTVB_HD void tile_stage_plane(const TileCtx<T>& c, const TileGeom& g, const ImgView<T>& X, const Params<T>& P, int q, int tid) {
     const int lane = tid & 31, wid = tid >> 5, nwarps = g.nthreads >> 5;
     const T* plane = X.row(P, tile_clamp_plane(P, q), 0, 0);
-    T* slot = c.Xs + (long long)tile_slot(q) * g.FC * g.slotX;
+    T* slot = c.Xs + (long long)tile_slot(q) * g.xslot;
     const int cj = -VEC + lane * VEC;                 // tile column of this lane's quad
     const int gj0 = c.j0 + cj;
     const bool vec_ok = VEC > 1 && gj0 >= 0 && gj0 + VEC <= P.Nj;
@@ -138,6 +209,83 @@ PYTVB_HD void tile_stage_plane(const TileCtx<T>& c, const TileGeom& g, const Img
         for (int rq = wid; rq < nrows; rq += nwarps) stage_copy<sizeof(T)>(slot + c.rowd[rq] + dcol, plane + c.rowg[rq] + gcol);
     }
 }
+
+// ---- staging by TMA (vector path).  The per-thread copies above cost 37 % of the kernel's instructions and of its stall
+// samples (table look-ups, 64-bit addresses, one LDGSTS per quad; profiles/r02f_tv_tile_sass_mix.txt).  With a tensor map of
+// the (planes, M, Ni, Nj) image one thread issues ONE cp.async.bulk.tensor per plane for the whole (FC, rowsX, pitchX) box
+// and the other threads spend nothing.  TMA fills cells outside the tensor with ZEROS, which is the wrong boundary rule
+// here (core.cuh), so the CTAs whose window reaches outside the image (c.fix) repair the window once it has landed:
+// every out-of-range cell takes the value of the cell with both indices clamped (always an in-range cell of the same
+// frame and window, so the repair reads only cells TMA wrote and writes only cells it zero-filled: no ordering inside it).
+template <typename T, int VEC>
+PYTVB_HD void tile_fixup_plane(const TileCtx<T>& c, const TileGeom& g, const Params<T>& P, int q, int tid) {
+    const int lane = tid & 31, wid = tid >> 5, nwarps = g.nthreads >> 5;
+    T* slot = c.Xs + (long long)tile_slot(q) * g.xslot;
+    const int iw = c.i0 - 2, jw = c.j0 - 2 * VEC;           // image row / column of window cell (0, 0)
+    const int nrows = g.FC * g.rowsX, nq = g.pitchX / VEC;
+    const bool cols_in = jw >= 0 && jw + g.pitchX <= P.Nj;
+    for (int rq = wid; rq < nrows; rq += nwarps) {
+        const int fl = rq / g.rowsX, xr = rq - fl * g.rowsX;
+        const int gi = iw + xr, ci = clampi(gi, 0, P.Ni - 1);
+        if (ci == gi && cols_in) continue;
+        const T* src = slot + (long long)fl * g.slotX + (ci - iw) * g.pitchX;
+        T* dst = slot + (long long)fl * g.slotX + xr * g.pitchX;
+        for (int k = lane; k < nq; k += 32) {
+            const int gj = jw + k * VEC;
+            if (ci == gi && gj >= 0 && gj + VEC <= P.Nj) continue;      // Nj % VEC == 0: a quad is in or out as a whole
+            Pack<T, VEC> v;
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) v.v[e] = src[clampi(gj + e, 0, P.Nj - 1) - jw];
+            st_pack<T, VEC>(dst + k * VEC, v);
+        }
+    }
+}
+
+// What the TMA load leaves in the window, as plain code (host emulation of the vector path: tests/emul).
+template <typename T, int VEC>
+PYTVB_HD void tile_stage_plane_zfill(const TileCtx<T>& c, const TileGeom& g, const ImgView<T>& X, const Params<T>& P, int q, int tid) {
+    T* slot = c.Xs + (long long)tile_slot(q) * g.xslot;
+    const int ql = tile_clamp_plane(P, q);
+    const int iw = c.i0 - 2, jw = c.j0 - 2 * VEC;
+    const int ncell = g.FC * g.rowsX * g.pitchX;
+    for (int k = tid; k < ncell; k += g.nthreads) {
+        const int fl = k / g.slotX, rem = k - fl * g.slotX, xr = rem / g.pitchX, xc = rem - xr * g.pitchX;
+        const int gi = iw + xr, gj = jw + xc;
+        const bool in = gi >= 0 && gi < P.Ni && gj >= 0 && gj < P.Nj;
+        slot[(long long)fl * g.slotX + rem] = in ? X.row(P, ql, c.t0 + fl, gi)[gj] : T(0);
+    }
+}
+
+#if defined(__CUDACC__)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// Generic-proxy accesses to shared memory (the phases' reads, the repair's writes) before this point are ordered before
+// the async-proxy writes of a TMA load issued after it.
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// One (FC, rowsX, pitchX) box of plane `zi` of the tensor behind `map` -> dst; completion is counted in bytes on `bar`.
+__device__ __forceinline__ void tma_load_4d(void* dst, const void* map, unsigned long long* bar, int cj, int ci, int ct, int cz) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(cj), "r"(ci), "r"(ct), "r"(cz)
+                 : "memory");
+}
+#endif
 
 // Static-mask bytes of the work region (clamped), once per CTA.
 template <typename T, int VEC>
@@ -204,23 +352,20 @@ PYTVB_HD void tile_time_scale(T* f, const TileCtx<T>& c, const Params<T>& P, con
 template <typename T>
 PYTVB_HD T cen_exists(long long k, long long L) { return (k >= 1 && k <= L - 2) ? T(1) : T(0); }
 
-// w = 1/|D x| (0 where the norm is 0) and the norm itself from the sum of squares: one MUFU, one select.
-// nr = sqrt(s) / div = s * w * k2 with k2 = 1/div^2 (w = div / sqrt(s)), which is 0 by itself where w was forced to 0.
+// w = 1/|D x| (0 where the norm is 0) from the sum of squares: one MUFU, one select.
 template <typename T>
-PYTVB_HD void tile_norm(T s, const Params<T>& P, T k2, T& nr, T& w, bool& pos) {
+PYTVB_HD void tile_norm(T s, const Params<T>& P, T& w, bool& pos) {
     const T rs = fast_rsqrt(s);
     pos = s > T(0);
     w = pos ? rs * P.div : T(0);
-    nr = s * w * k2;
 }
 #if defined(__CUDA_ARCH__)
 template <>
-__device__ __forceinline__ void tile_norm<float>(float s, const Params<float>& P, float k2, float& nr, float& w, bool& pos) {
+__device__ __forceinline__ void tile_norm<float>(float s, const Params<float>& P, float& w, bool& pos) {
     float rs;     // a sum of squares below FLT_MIN (all differences < 1.1e-19) counts as zero, as in norm_finish
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(fmaxf(s, 1.17549435e-38f)));
     pos = s >= 1.17549435e-38f;
     w = pos ? rs * P.div : 0.0f;
-    nr = s * w * k2;
 }
 #endif
 
@@ -230,7 +375,7 @@ PYTVB_HD void tile_init_z(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const 
                           const TilePos& tp) {
     constexpr int PX = TileC<VEC>::PX;
     const int qm = tile_clamp_plane(P, p - 1);
-    const T* Xp = c.Xs + ((long long)tile_slot(p) * g.FC + tp.fl) * g.slotX;
+    const T* Xp = c.Xs + (long long)tile_slot(p) * g.xslot + (long long)tp.fl * g.slotX;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int rr = tp.rr0 + r;
@@ -245,6 +390,37 @@ PYTVB_HD void tile_init_z(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const 
     }
 }
 
+// Elements just left / right of a thread's quad in its row.  A warp covers the 32 consecutive quads of one window row, so
+// on the device they come from the neighbouring lanes' registers (two shuffles); only lanes 0 / 31 read them from the
+// window (`edge` = the window has them: the scalar halo columns of x; not for w, where the halo lanes' results are unused and
+// the quad's own end element stands in).  The scalar loads this replaces had 4-way bank conflicts (lane stride 4 words): 24
+// of the 64 shared-memory wavefronts per row and warp (profiles/r02f_*).  N elements per side (1, or 2 for the centred
+// column terms): l[0] = element -1, l[1] = element -2; r[0] = element VEC, r[1] = element VEC+1.  `lane` = the quad's index
+// in the row.  The host emulation reads the window where the device shuffles.
+template <typename T, int VEC, int N>
+PYTVB_HD void quad_sides(T* l, T* r, const T* q, const T* row, int lane, bool edge) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+#if defined(__CUDA_ARCH__)
+        const T sl = __shfl_up_sync(0xffffffffu, q[VEC - 1 - k], 1), sr = __shfl_down_sync(0xffffffffu, q[k], 1);
+#else
+        const T sl = lane > 0 ? row[-1 - k] : T(0), sr = lane < 31 ? row[VEC + k] : T(0);
+#endif
+        l[k] = lane > 0 ? sl : ((edge && k == 0) ? row[-1] : q[0]);
+        r[k] = lane < 31 ? sr : ((edge && k == 0) ? row[VEC] : q[VEC - 1]);
+    }
+}
+
+// S(w_k, w_{k+1}) of an edge term for a whole quad (pair_w element-wise).
+template <typename T, int VEC, int SCHEME>
+PYTVB_HD void vpair_w(T* d, const T* wk, const T* wk1) {
+    if (SCHEME == HYBRID) VOp<T, VEC>::add(d, wk, wk1);
+    else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) d[e] = SCHEME == UPWIND ? wk[e] : wk1[e];
+    }
+}
+
 // ---- w-phase of plane p.  Outputs: w(p) to shared memory, norms (optional) and the TV partial sum for output voxels, and -
 // with the z axis on - the finished G(p-1).
 // Register diet (the kernel is instruction-issue bound, 128 registers per thread at 16 warps per SM): the z edge term is
@@ -255,15 +431,16 @@ template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, int TSMO
 PYTVB_HD void tile_phase_w(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const TileGeom& g, const Params<T>& P, const ImgView<T>& TS,
                            T* G, T* norms, int p, const TilePos& tp) {
     typedef Comp<SCHEME, Z_ON, T_ON> C;
+    typedef VOp<T, VEC> V;
     constexpr bool FWD = C::NEED_FWD, BWD = C::NEED_BWD, CEN = SCHEME == CENTRAL;
     constexpr int PX = TileC<VEC>::PX, WJ = TileC<VEC>::WJ;
     const int sp = tile_slot(p);
     const int xo = (tp.rr0 + 2) * PX + tp.cj + 2 * VEC;        // own quad in an x window, work row 0
-    const T* Xp = c.Xs + ((long long)sp * g.FC + tp.fl) * g.slotX + xo;
-    const T* Xn = c.Xs + ((long long)tile_slot(p + 1) * g.FC + tp.fl) * g.slotX + xo;
+    const T* Xp = c.Xs + (long long)sp * g.xslot + (long long)tp.fl * g.slotX + xo;
+    const T* Xn = c.Xs + (long long)tile_slot(p + 1) * g.xslot + (long long)tp.fl * g.slotX + xo;
     const int flm = tp.fl > 0 ? tp.fl - 1 : tp.fl, flp = tp.fl < g.FC - 1 ? tp.fl + 1 : tp.fl;
-    const T* Xtm = c.Xs + ((long long)sp * g.FC + flm) * g.slotX + xo;
-    const T* Xtp = c.Xs + ((long long)sp * g.FC + flp) * g.slotX + xo;
+    const T* Xtm = c.Xs + (long long)sp * g.xslot + (long long)flm * g.slotX + xo;
+    const T* Xtp = c.Xs + (long long)sp * g.xslot + (long long)flp * g.slotX + xo;
     T* Wp = c.Ws + (long long)tp.fl * g.slotW + (tp.rr0 + 1) * WJ + tp.cj + VEC;
     const int t = tp.t;
     const int ql = tile_clamp_plane(P, p);
@@ -272,6 +449,7 @@ PYTVB_HD void tile_phase_w(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
     const T rz2 = P.srz * P.srz, rt2 = P.srt * P.srt, k2 = P.inv_div * P.inv_div;
     const T fz = CEN ? cen_exists<T>(zg, P.NzG) : T(1), ft = CEN ? cen_exists<T>(t, P.M) : T(1);
     T* Gq = G + (long long)(p - 1) * P.sZ + tp.goff;            // G(p-1) at the thread's quad, work row 0
+    const int lane = tp.cj / VEC + 1;
     T tvstep = T(0);
     T xu[VEC], xc[VEC];
     ld_into<T, VEC>(xu, Xp - PX);
@@ -281,85 +459,86 @@ PYTVB_HD void tile_phase_w(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
         const int rr = tp.rr0 + r, gi = c.i0 + rr;
         T xd[VEC], s[VEC];
         ld_into<T, VEC>(xd, Xp + (r + 1) * PX);
-        const T cl = Xp[r * PX - 1], cr = Xp[r * PX + VEC];
+        T cl, cr;
+        quad_sides<T, VEC, 1>(&cl, &cr, xc, Xp + r * PX, lane, true);
         if (!CEN) {
+            // column differences: VEC + 1 of them serve the forward and the backward component of the quad
+            T djf[VEC], djb[VEC];
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                s[e] = T(0);
-                if (FWD) {
-                    const T di = xd[e] - xc[e], dj = (e + 1 < VEC ? xc[e + 1 < VEC ? e + 1 : e] : cr) - xc[e];
-                    s[e] = di * di;
-                    s[e] += dj * dj;
-                }
-                if (BWD) {
-                    const T di = xc[e] - xu[e], dj = xc[e] - (e > 0 ? xc[e > 0 ? e - 1 : 0] : cl);
-                    s[e] += di * di;
-                    s[e] += dj * dj;
-                }
+            for (int e = 0; e < VEC; ++e) djf[e] = (e + 1 < VEC ? xc[e + 1 < VEC ? e + 1 : e] : cr) - xc[e];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) djb[e] = e > 0 ? (FWD ? djf[e > 0 ? e - 1 : 0] : xc[e] - xc[e > 0 ? e - 1 : 0]) : xc[0] - cl;
+            T di[VEC];
+            if (FWD) {
+                V::sub(di, xd, xc);
+                V::mul(s, di, di);
+                V::fma(s, djf, djf, s);
+            }
+            if (BWD) {
+                V::sub(di, xc, xu);
+                if (FWD) V::fma(s, di, di, s); else V::mul(s, di, di);
+                V::fma(s, djb, djb, s);
             }
         } else {
             const T fi = cen_exists<T>(gi, P.Ni);
+            T di[VEC], dj[VEC];
+            V::sub(di, xd, xu);
+            V::muls(di, di, fi);
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
                 const T fj = cen_exists<T>(c.j0 + tp.cj + e, P.Nj);
-                const T di = fi * (xd[e] - xu[e]);
-                const T dj = fj * ((e + 1 < VEC ? xc[e + 1 < VEC ? e + 1 : e] : cr) - (e > 0 ? xc[e > 0 ? e - 1 : 0] : cl));
-                s[e] = di * di;
-                s[e] += dj * dj;
+                dj[e] = fj * ((e + 1 < VEC ? xc[e + 1 < VEC ? e + 1 : e] : cr) - (e > 0 ? xc[e > 0 ? e - 1 : 0] : cl));
             }
+            V::mul(s, di, di);
+            V::fma(s, dj, dj, s);
         }
         T dzf[VEC];       // one-sided / hybrid: x(p+1) - x(p);  centred: x(p+1) - x(p-1), 0 where it does not exist
         if (Z_ON) {
-            T xn[VEC];
+            T xn[VEC], q[VEC];
             ld_into<T, VEC>(xn, Xn + r * PX);
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                if (!CEN) {
-                    dzf[e] = xn[e] - xc[e];
-                    T q = T(0);
-                    if (FWD) q = dzf[e] * dzf[e];
-                    if (BWD) q += st.a[r][e] * st.a[r][e];
-                    s[e] += rz2 * q;
-                } else {
-                    dzf[e] = fz * (xn[e] - st.a[r][e]);
-                    s[e] += rz2 * (dzf[e] * dzf[e]);
-                }
+            if (!CEN) {
+                V::sub(dzf, xn, xc);
+                if (FWD) V::mul(q, dzf, dzf);
+                if (BWD) { if (FWD) V::fma(q, st.a[r], st.a[r], q); else V::mul(q, st.a[r], st.a[r]); }
+            } else {
+                V::sub(dzf, xn, st.a[r]);
+                V::muls(dzf, dzf, fz);
+                V::mul(q, dzf, dzf);
             }
+            V::fmas(s, q, rz2, s);
         }
         if (T_ON) {
-            T xm[VEC], xp[VEC], q[VEC];
+            T xm[VEC], xp[VEC], q[VEC], d[VEC];
             ld_into<T, VEC>(xm, Xtm + r * PX);
             ld_into<T, VEC>(xp, Xtp + r * PX);
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                if (!CEN) {
-                    q[e] = T(0);
-                    if (FWD) { const T d = xp[e] - xc[e]; q[e] = d * d; }
-                    if (BWD) { const T d = xc[e] - xm[e]; q[e] += d * d; }
-                } else {
-                    const T d = ft * (xp[e] - xm[e]);
-                    q[e] = d * d;
-                }
+            if (!CEN) {
+                if (FWD) { V::sub(d, xp, xc); V::mul(q, d, d); }
+                if (BWD) { V::sub(d, xc, xm); if (FWD) V::fma(q, d, d, q); else V::mul(q, d, d); }
+            } else {
+                V::sub(d, xp, xm);
+                V::muls(d, d, ft);
+                V::mul(q, d, d);
             }
             if constexpr (TSMODE == 0) {
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) s[e] += rt2 * q[e];
+                V::fmas(s, q, rt2, s);
             } else {
                 T fac[VEC];
                 tile_time_factor<T, VEC, TSMODE>(fac, c, g, P, TS, rr + 1, tp.cj, ql, t);
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) { const T wt = P.srt * fac[e]; s[e] += (wt * wt) * q[e]; }
+                V::muls(fac, fac, P.srt);
+                V::mul(fac, fac, fac);
+                V::fma(s, fac, q, s);
             }
         }
         Pack<T, VEC> wq;
         T nrv[VEC];
         bool posv[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) tile_norm<T>(s[e], P, wq.v[e], posv[e]);
+        V::mul(nrv, s, wq.v);             // |D x| = sqrt(s) / div = s * w / div^2, 0 by itself where w was forced to 0
+        V::muls(nrv, nrv, k2);
         T rowsum = T(0);
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-            tile_norm<T>(s[e], P, k2, nrv[e], wq.v[e], posv[e]);
-            rowsum += nrv[e];
-        }
+        for (int e = 0; e < VEC; ++e) rowsum += nrv[e];
         st_pack<T, VEC>(Wp + r * WJ, wq);
         const bool row_out = rr >= 0 && rr < g.TI && gi < P.Ni;        // warp-uniform
         if (plane_out && row_out && tp.col_out) {
@@ -374,18 +553,25 @@ PYTVB_HD void tile_phase_w(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
         if (Z_ON) {
             // z edge term between planes p-1 and p (centred: Cz(p)); it completes G(p-1)
             Pack<T, VEC> gq;
+            T en[VEC];
+            if (!CEN) {
+                T sw[VEC];
+                vpair_w<T, VEC, SCHEME>(sw, st.w[r], wq.v);
+                V::mul(en, st.a[r], sw);
+                V::muls(en, en, P.srz);
+                V::sub(gq.v, st.g[r], en);
+                V::muls(gq.v, gq.v, k2);
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                if (!CEN) {
-                    const T en = P.srz * (st.a[r][e] * pair_w<T, SCHEME>(st.w[r][e], wq.v[e]));
-                    gq.v[e] = (st.g[r][e] - en) * k2;
-                    st.g[r][e] = en;
-                    st.a[r][e] = dzf[e];
-                } else {
-                    const T cz = P.srz * (dzf[e] * wq.v[e]);
-                    gq.v[e] = (st.g[r][e] - cz) * k2;
+                for (int e = 0; e < VEC; ++e) { st.g[r][e] = en[e]; st.a[r][e] = dzf[e]; }
+            } else {
+                V::mul(en, dzf, wq.v);
+                V::muls(en, en, P.srz);
+                V::sub(gq.v, st.g[r], en);
+                V::muls(gq.v, gq.v, k2);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
                     st.g[r][e] = st.e[r][e];        // srz * Cz(p-1): the incoming z term of G(p)
-                    st.e[r][e] = cz;
+                    st.e[r][e] = en[e];
                     st.a[r][e] = xc[e];
                 }
             }
@@ -401,17 +587,17 @@ PYTVB_HD void tile_phase_w(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
 template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, int TSMODE>
 PYTVB_HD void tile_phase_g(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const TileGeom& g, const Params<T>& P, const ImgView<T>& TS, T* G, int p,
                            const TilePos& tp) {
+    typedef VOp<T, VEC> V;
     constexpr bool CEN = SCHEME == CENTRAL;
     constexpr int PX = TileC<VEC>::PX, WJ = TileC<VEC>::WJ;
     const int sp = tile_slot(p);
     const int xcol = tp.cj + 2 * VEC, wcol = tp.cj + VEC;
     const int xo0 = (tp.rr0 + 2) * PX + xcol, wo0 = (tp.rr0 + 1) * WJ + wcol;       // own quad, work row 0
-    const T* Xp = c.Xs + ((long long)sp * g.FC + tp.fl) * g.slotX + xo0;
+    const T* Xp = c.Xs + (long long)sp * g.xslot + (long long)tp.fl * g.slotX + xo0;
     const T* Wp = c.Ws + (long long)tp.fl * g.slotW + wo0;
     const int t = tp.t;
     const T k2 = P.inv_div * P.inv_div;
-    // halo lanes (first / last quad of the work columns) have no left / right neighbour in the w window: clamp (results unused)
-    const int wl = wcol > 0 ? -1 : 0, wr = wcol + VEC < WJ ? VEC : VEC - 1;
+    const int lane = tp.cj / VEC + 1;      // halo lanes (0 and 31) have no outer neighbour in the w window: their results are unused
     bool have = false;
     T tdn[VEC];          // one-sided / hybrid: row term (rr -> rr+1) of the previous row
     T cu[VEC], cc[VEC];  // centred: C_i(rr-1), C_i(rr)
@@ -431,13 +617,14 @@ PYTVB_HD void tile_phase_g(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
         for (int e = 0; e < VEC; ++e) wc[e] = st.w[r][e];
         // ---- rows
         if (!CEN) {
-            T xd[VEC], wd[VEC], tup[VEC];
+            T xd[VEC], wd[VEC], tup[VEC], dx[VEC], sw[VEC];
             if (!have) {
                 T xu[VEC], wu[VEC];
                 ld_into<T, VEC>(xu, xrow - PX);
                 ld_into<T, VEC>(wu, wrow - WJ);
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) tup[e] = (xc[e] - xu[e]) * pair_w<T, SCHEME>(wu[e], wc[e]);
+                V::sub(dx, xc, xu);
+                vpair_w<T, VEC, SCHEME>(sw, wu, wc);
+                V::mul(tup, dx, sw);
             } else {
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) tup[e] = tdn[e];
@@ -447,14 +634,13 @@ PYTVB_HD void tile_phase_g(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) wd[e] = st.w[r + 1 < R ? r + 1 : r][e];
             } else ld_into<T, VEC>(wd, wrow + WJ);
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                tdn[e] = (xd[e] - xc[e]) * pair_w<T, SCHEME>(wc[e], wd[e]);
-                gq[e] = tup[e] - tdn[e];
-            }
+            V::sub(dx, xd, xc);
+            vpair_w<T, VEC, SCHEME>(sw, wc, wd);
+            V::mul(tdn, dx, sw);
+            V::sub(gq, tup, tdn);
         } else {
             // C_i(m) = exists(m) * (x(m+1) - x(m-1)) * w(m);  G_i(rr) = C_i(rr-1) - C_i(rr+1)
-            T xu[VEC], xd[VEC], xd2[VEC], wd[VEC], cd[VEC];
+            T xu[VEC], xd[VEC], xd2[VEC], wd[VEC], cd[VEC], dx[VEC];
             ld_into<T, VEC>(xd, xrow + PX);
             ld_into<T, VEC>(xd2, xrow + 2 * PX);
             if (!have) {
@@ -463,29 +649,31 @@ PYTVB_HD void tile_phase_g(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
                 ld_into<T, VEC>(xu2, xrow - 2 * PX);
                 ld_into<T, VEC>(wu, wrow - WJ);
                 const T fu = cen_exists<T>(gi - 1, P.Ni), fc = cen_exists<T>(gi, P.Ni);
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) {
-                    cu[e] = fu * ((xc[e] - xu2[e]) * wu[e]);
-                    cc[e] = fc * ((xd[e] - xu[e]) * wc[e]);
-                }
+                V::sub(dx, xc, xu2);
+                V::mul(cu, dx, wu);
+                V::muls(cu, cu, fu);
+                V::sub(dx, xd, xu);
+                V::mul(cc, dx, wc);
+                V::muls(cc, cc, fc);
             }
             if (r + 1 < R) {
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) wd[e] = st.w[r + 1 < R ? r + 1 : r][e];
             } else ld_into<T, VEC>(wd, wrow + WJ);
             const T fd = cen_exists<T>(gi + 1, P.Ni);
+            V::sub(dx, xd2, xc);
+            V::mul(cd, dx, wd);
+            V::muls(cd, cd, fd);
+            V::sub(gq, cu, cd);
 #pragma unroll
-            for (int e = 0; e < VEC; ++e) {
-                cd[e] = fd * ((xd2[e] - xc[e]) * wd[e]);
-                gq[e] = cu[e] - cd[e];
-                cu[e] = cc[e];
-                cc[e] = cd[e];
-            }
+            for (int e = 0; e < VEC; ++e) { cu[e] = cc[e]; cc[e] = cd[e]; }
         }
         have = true;
-        // ---- columns
+        // ---- columns (element-shifted within the quad: scalar code)
         if (!CEN) {
-            const T xl = xrow[-1], xr = xrow[VEC], wlv = wrow[wl], wrv = wrow[wr];
+            T xl, xr, wlv, wrv;
+            quad_sides<T, VEC, 1>(&xl, &xr, xc, xrow, lane, true);
+            quad_sides<T, VEC, 1>(&wlv, &wrv, wc, wrow, lane, false);
             T tj = (xc[0] - xl) * pair_w<T, SCHEME>(wlv, wc[0]);
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
@@ -499,9 +687,10 @@ PYTVB_HD void tile_phase_g(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
             T xw[VEC + 4], ww[VEC + 2];
 #pragma unroll
             for (int e = 0; e < VEC; ++e) { xw[e + 2] = xc[e]; ww[e + 1] = wc[e]; }
-            const int xl2 = xcol - 2 >= 0 ? -2 : -xcol, xr2 = xcol + VEC + 1 < PX ? VEC + 1 : PX - 1 - xcol;
-            xw[0] = xrow[xl2]; xw[1] = xrow[-1]; xw[VEC + 2] = xrow[VEC]; xw[VEC + 3] = xrow[xr2];
-            ww[0] = wrow[wl]; ww[VEC + 1] = wrow[wr];
+            T xs_l[2], xs_r[2];
+            quad_sides<T, VEC, 2>(xs_l, xs_r, xc, xrow, lane, true);
+            xw[0] = xs_l[1]; xw[1] = xs_l[0]; xw[VEC + 2] = xs_r[0]; xw[VEC + 3] = xs_r[1];
+            quad_sides<T, VEC, 1>(&ww[0], &ww[VEC + 1], wc, wrow, lane, false);
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
                 const int gj = c.j0 + tp.cj + e;
@@ -513,7 +702,7 @@ PYTVB_HD void tile_phase_g(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
         // ---- time
         if (T_ON) {
             const int dm = tp.fl > 0 ? -1 : 0, dp = tp.fl < g.FC - 1 ? 1 : 0;          // neighbouring frames, clamped
-            T xm[VEC], xp[VEC], wm[VEC], wp[VEC], wq[VEC], v[VEC];
+            T xm[VEC], xp[VEC], wm[VEC], wp[VEC], wq[VEC], v[VEC], v2[VEC], dx[VEC], sw[VEC];
             ld_into<T, VEC>(wm, wrow + dm * g.slotW);
             ld_into<T, VEC>(wp, wrow + dp * g.slotW);
 #pragma unroll
@@ -521,29 +710,36 @@ PYTVB_HD void tile_phase_g(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
             if constexpr (TSMODE == 2) {   // along t the inverse norms travel with their voxel's scale (strip_quad_G_impl)
                 T f[VEC];
                 tile_time_scale<T, VEC>(f, c, P, TS, rr + 1, tp.cj, p, t + dm);
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) wm[e] *= f[e];
+                V::mul(wm, wm, f);
                 tile_time_scale<T, VEC>(f, c, P, TS, rr + 1, tp.cj, p, t);
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) wq[e] *= f[e];
+                V::mul(wq, wq, f);
                 tile_time_scale<T, VEC>(f, c, P, TS, rr + 1, tp.cj, p, t + dp);
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) wp[e] *= f[e];
+                V::mul(wp, wp, f);
             }
             if (!CEN) {
                 ld_into<T, VEC>(xm, xrow + dm * g.slotX);
                 ld_into<T, VEC>(xp, xrow + dp * g.slotX);
-#pragma unroll
-                for (int e = 0; e < VEC; ++e)
-                    v[e] = P.srt * ((xc[e] - xm[e]) * pair_w<T, SCHEME>(wm[e], wq[e]) - (xp[e] - xc[e]) * pair_w<T, SCHEME>(wq[e], wp[e]));
+                V::sub(dx, xc, xm);
+                vpair_w<T, VEC, SCHEME>(sw, wm, wq);
+                V::mul(v, dx, sw);
+                V::sub(dx, xp, xc);
+                vpair_w<T, VEC, SCHEME>(sw, wq, wp);
+                V::mul(v2, dx, sw);
+                V::sub(v, v, v2);
+                V::muls(v, v, P.srt);
             } else {
                 // C_t(t-1) = exists(t-1) (x(t) - x(t-2)) w(t-1);  C_t(t+1) = exists(t+1) (x(t+2) - x(t)) w(t+1)
                 const int dm2 = tp.fl > 1 ? -2 : -tp.fl, dp2 = tp.fl < g.FC - 2 ? 2 : g.FC - 1 - tp.fl;
                 ld_into<T, VEC>(xm, xrow + dm2 * g.slotX);
                 ld_into<T, VEC>(xp, xrow + dp2 * g.slotX);
                 const T am = P.srt * cen_exists<T>(t - 1, P.M), ap = P.srt * cen_exists<T>(t + 1, P.M);
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) v[e] = am * ((xc[e] - xm[e]) * wm[e]) - ap * ((xp[e] - xc[e]) * wp[e]);
+                V::sub(dx, xc, xm);
+                V::mul(v, dx, wm);
+                V::muls(v, v, am);
+                V::sub(dx, xp, xc);
+                V::mul(v2, dx, wp);
+                V::muls(v2, v2, ap);
+                V::sub(v, v, v2);
             }
             if constexpr (TSMODE >= 1) {
                 if (c.Ms) {
@@ -552,17 +748,14 @@ PYTVB_HD void tile_phase_g(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
                     for (int e = 0; e < VEC; ++e) v[e] *= m[e] ? P.sfac : T(1);
                 }
             }
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) gq[e] += v[e];
+            V::add(gq, gq, v);
         }
         if (Z_ON) {
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) st.g[r][e] += gq[e];
+            V::add(st.g[r], st.g[r], gq);
         } else {
             if (tp.col_out && gi < P.Ni) {
                 Pack<T, VEC> pk;
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) pk.v[e] = gq[e] * k2;
+                V::muls(pk.v, gq, k2);
                 st_pack<T, VEC>(G + (long long)p * P.sZ + tp.goff + (long long)r * P.Nj, pk);
             }
         }

@@ -9,21 +9,44 @@
 
 namespace pytvb {
 
-// PYTVB_TV_PATH=sweeps forces the fallback (A/B measurements); read once per process.
-inline bool tv_force_sweeps() {
-    static const bool v = [] { const char* e = getenv("PYTVB_TV_PATH"); return e && strcmp(e, "sweeps") == 0; }();
+// PYTVB_TV_PATH = auto (default) | tile | sweeps; read once per process.
+enum TvPathMode { TV_AUTO = 0, TV_TILE = 1, TV_SWEEPS = 2 };
+inline TvPathMode tv_path_mode() {
+    static const TvPathMode v = [] {
+        const char* e = getenv("PYTVB_TV_PATH");
+        if (e && strcmp(e, "sweeps") == 0) return TV_SWEEPS;
+        if (e && strcmp(e, "tile") == 0) return TV_TILE;
+        return TV_AUTO;
+    }();
     return v;
 }
 
-inline bool tv_uses_tile(const pytvb_problem* pb) {
-    if (tv_force_sweeps()) return false;
+// Can the tile kernel take the problem at all?
+inline bool tv_tile_possible(const pytvb_problem* pb) {
     const Axes ax = axes_of(pb);
-    // the centred scheme on a length-2 axis degrades to forward differences there (tv_operators_CPU.py:339,347): fallback only
+    // the centred scheme on a length-2 axis degrades to forward differences there (tv_operators_CPU.py:339,347): two-sweep form only
     if (pb->scheme == PYTVB_CENTRAL && ((ax.z_on && pb->Nz_global == 2) || (ax.t_on && pb->M == 2))) return false;
     TileGeom g;
     const bool mask = ax.t_on && pb->mask_static;
     if (pb->dtype == PYTVB_F32) return make_tile_geom<float, 4, PYTVB_TILE_R>(g, (int)pb->Nz, (int)pb->M, (int)pb->Ni, (int)pb->Nj, ax.t_on, mask);
     return make_tile_geom<double, 2, PYTVB_TILE_R>(g, (int)pb->Nz, (int)pb->M, (int)pb->Ni, (int)pb->Nj, ax.t_on, mask);
+}
+
+// Which form runs.  Both are parity-green on every golden; the choice is measured speed (profiles/r02g_tv_times.txt,
+// C4 slab, ms: hybrid 3.13 tile / 2.68 sweeps, upwind 2.78 / 2.29, centred 3.47 / 3.67; 512^3 hybrid 1.00 / 0.64).  The tile kernel
+// moves 1.04 x the algorithmic 8 B/voxel (the sweeps 2.5 x) and needs no workspace, but it is bound by instruction issue at
+// the 16 warps per SM its 126 registers per thread allow, so on large volumes the occupancy of the two sweeps wins for the
+// one-sided and hybrid schemes.  auto: the tile kernel for the centred scheme, for weight maps on slabs with z halos (the
+// sweeps do not take them), and for volumes small enough to be launch-bound (one launch instead of two; no workspace).
+inline bool tv_uses_tile(const pytvb_problem* pb) {
+    const TvPathMode m = tv_path_mode();
+    if (m == TV_SWEEPS || !tv_tile_possible(pb)) return false;
+    if (m == TV_TILE) return true;
+    const Axes ax = axes_of(pb);
+    if (pb->scheme == PYTVB_CENTRAL) return true;
+    if (pb->time_scale && ax.z_on && ax.t_on && (pb->time_scale_lo || pb->time_scale_hi)) return true;
+    const long long V = (long long)pb->Nz * pb->M * pb->Ni * pb->Nj;
+    return V <= (1LL << 20);
 }
 
 // Most CTAs (= TV partial sums) the tile kernel can launch for this problem, over its vector and scalar forms.

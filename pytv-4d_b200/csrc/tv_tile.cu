@@ -2,6 +2,7 @@
 #include "host_common.cuh"
 #include "tv_path.cuh"
 #include "tv_args.cuh"
+#include "tmap.cuh"
 
 using namespace pytvb;
 
@@ -16,7 +17,16 @@ int launch_tile(const TvArgs<T>& a, const TileGeom& g, size_t smem) {
         PYTVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_LIMIT));
         attr_set = true;
     }
-    kern<<<(unsigned)g.nblocks, g.nthreads, smem, a.st>>>(a.X, a.TS, a.G, a.norms, a.partial, a.P, g);
+    // tensor maps of the image and of its two halo-plane buffers (vector path: staged by TMA; the scalar path copies per thread)
+    CUtensorMap mx, mlo, mhi;
+    const bool tma = VEC > 1;
+    const int rc0 = make_image_tmap<T>(&mx, tma ? a.X.base : nullptr, a.P.Nz, a.P.M, a.P.Ni, a.P.Nj, g.FC, g.rowsX, g.pitchX);
+    if (rc0 != PYTVB_OK) return rc0;
+    const int rc1 = make_image_tmap<T>(&mlo, tma ? a.X.lo : nullptr, a.X.depth, a.P.M, a.P.Ni, a.P.Nj, g.FC, g.rowsX, g.pitchX);
+    if (rc1 != PYTVB_OK) return rc1;
+    const int rc2 = make_image_tmap<T>(&mhi, tma ? a.X.hi : nullptr, a.X.depth, a.P.M, a.P.Ni, a.P.Nj, g.FC, g.rowsX, g.pitchX);
+    if (rc2 != PYTVB_OK) return rc2;
+    kern<<<(unsigned)g.nblocks, g.nthreads, smem, a.st>>>(a.X, a.TS, a.G, a.norms, a.partial, a.P, g, mx, mlo, mhi);
     count_launches(1);
     PYTVB_CUDA(cudaGetLastError());
     *a.nblocks_out = g.nblocks;

@@ -254,6 +254,7 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct ETile {
         if (!make_tile_geom<T, VEC, R>(g, a.P.Nz, a.P.M, a.P.Ni, a.P.Nj, TT, mask)) return -20;
         if (g_tile_strips > 0 && g_tile_strips < g.strips) {
             g.strips = g_tile_strips; g.RPF = g.strips * R; g.TI = g.RPF - 2; g.rowsX = g.RPF + 2; g.slotX = g.rowsX * g.pitchX; g.slotW = g.RPF * g.WJ;
+            g.xslot = (int)((((size_t)g.FC * g.slotX * sizeof(T) + 127) & ~size_t(127)) / sizeof(T));
             g.nthreads = 32 * g.FC * g.strips; g.nti = (a.P.Ni + g.TI - 1) / g.TI;
             g.nblocks = (long long)g.nti * g.ntj * g.nfg * g.nzc;
         }
@@ -267,11 +268,17 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct ETile {
         constexpr int R = PYTVB_TILE_R;
         constexpr int TSM = TT ? TSMODE : 0;
         std::vector<unsigned char> smem(tile_smem_bytes<T>(g, mask) + 16);
+        // staging as on the device: the vector path by TMA (zero fill outside the image, then the repair of the border CTAs), the scalar
+        // path by clamped per-thread copies
+        auto stage = [&](const TileCtx<T>& c, int q, int tid) {
+            if (VEC > 1) tile_stage_plane_zfill<T, VEC>(c, g, a.X, a.P, q, tid); else tile_stage_plane<T, VEC>(c, g, a.X, a.P, q, tid);
+        };
+        auto land = [&](const TileCtx<T>& c, int q, int tid) { if (VEC > 1 && c.fix) tile_fixup_plane<T, VEC>(c, g, a.P, q, tid); };
         std::vector<TileThread<T, VEC, R>> st(g.nthreads);
         double tv = 0;
         for (long long b = 0; b < g.nblocks; ++b) {
             std::fill(smem.begin(), smem.end(), (unsigned char)0xFF);      // NaN pattern: an unstaged element shows up in the results
-            const TileCtx<T> c = tile_ctx<T>(g, b, a.P.Nz, smem.data(), mask);
+            const TileCtx<T> c = tile_ctx<T, VEC>(g, b, a.P, smem.data(), mask);
             for (auto& s : st) memset(&s, 0, sizeof(s));
             std::vector<TilePos> tps(g.nthreads);
             for (int tid = 0; tid < g.nthreads; ++tid) tps[tid] = tile_pos<T, VEC, R>(c, g, a.P, tid);
@@ -280,25 +287,29 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct ETile {
             all([&](int tid) { tile_stage_tables<T>(c, g, a.P, tid); });
             if (Z) {
                 const int p0 = c.zc0 - 1, p1 = c.zc1;
-                all([&](int tid) { tile_stage_plane<T, VEC>(c, g, a.X, a.P, p0, tid); tile_stage_plane<T, VEC>(c, g, a.X, a.P, p0 + 1, tid); });
+                all([&](int tid) { stage(c, p0, tid); stage(c, p0 + 1, tid); });
+                all([&](int tid) { land(c, p0, tid); land(c, p0 + 1, tid); });
                 all([&](int tid) { tile_init_z<T, VEC, SCHEME, R>(st[tid], c, g, a.X, a.P, p0, tps[tid]); });
                 for (int p = p0; p <= p1; ++p) {
                     // the staging of plane p+2 is asynchronous on the device: it may land at any time before the end of the step.
                     // Emulate the two extremes on alternating steps: before the w-phase / after the G-phase.
                     const bool early = (p & 1) != 0;
-                    if (early && p + 2 <= p1 + 1) all([&](int tid) { tile_stage_plane<T, VEC>(c, g, a.X, a.P, p + 2, tid); });
+                    if (early && p + 2 <= p1 + 1) all([&](int tid) { stage(c, p + 2, tid); });
                     all([&](int tid) { tile_phase_w<T, VEC, SCHEME, Z, TT, R, TSM>(st[tid], c, g, a.P, a.W, a.out, a.out2, p, tps[tid]); });
                     if (p >= c.zc0 && p < c.zc1) all([&](int tid) { tile_phase_g<T, VEC, SCHEME, Z, TT, R, TSM>(st[tid], c, g, a.P, a.W, a.out, p, tps[tid]); });
-                    if (!early && p + 2 <= p1 + 1) all([&](int tid) { tile_stage_plane<T, VEC>(c, g, a.X, a.P, p + 2, tid); });
+                    if (!early && p + 2 <= p1 + 1) all([&](int tid) { stage(c, p + 2, tid); });
+                    if (p + 2 <= p1 + 1) all([&](int tid) { land(c, p + 2, tid); });
                 }
             } else {
-                all([&](int tid) { tile_stage_plane<T, VEC>(c, g, a.X, a.P, c.zc0, tid); });
+                all([&](int tid) { stage(c, c.zc0, tid); });
+                all([&](int tid) { land(c, c.zc0, tid); });
                 for (int p = c.zc0; p < c.zc1; ++p) {
                     const bool early = (p & 1) != 0;
-                    if (early && p + 1 < c.zc1) all([&](int tid) { tile_stage_plane<T, VEC>(c, g, a.X, a.P, p + 1, tid); });
+                    if (early && p + 1 < c.zc1) all([&](int tid) { stage(c, p + 1, tid); });
                     all([&](int tid) { tile_phase_w<T, VEC, SCHEME, Z, TT, R, TSM>(st[tid], c, g, a.P, a.W, a.out, a.out2, p, tps[tid]); });
                     all([&](int tid) { tile_phase_g<T, VEC, SCHEME, Z, TT, R, TSM>(st[tid], c, g, a.P, a.W, a.out, p, tps[tid]); });
-                    if (!early && p + 1 < c.zc1) all([&](int tid) { tile_stage_plane<T, VEC>(c, g, a.X, a.P, p + 1, tid); });
+                    if (!early && p + 1 < c.zc1) all([&](int tid) { stage(c, p + 1, tid); });
+                    if (p + 1 < c.zc1) all([&](int tid) { land(c, p + 1, tid); });
                 }
             }
             for (auto& s : st) tv += (double)s.tv;
@@ -328,7 +339,7 @@ int run(int op, const pytvb_problem* pb, const void* in, void* out, void* out2, 
         case 7: a.X = ImgView<T>{(const T*)in, (const T*)lo, (const T*)hi, 1}; return dispatch<ED2, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
         case 8: a.F = FieldView<T>{(const T*)in, (const T*)lo, (const T*)hi}; return dispatch<EDT2, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);
         case 10:
-            if (tv_uses_tile(pb)) {   // tile kernel: in = x, out = G, out2 = norms | NULL; lo / hi = two halo planes each; a.W carries the time-scale view
+            if (tv_tile_possible(pb)) {   // tile kernel: in = x, out = G, out2 = norms | NULL; lo / hi = two halo planes each; a.W carries the time-scale view
                 a.X = ImgView<T>{(const T*)in, (const T*)lo, (const T*)hi, 2};
                 a.W = ImgView<T>{a.P.tscale, (const T*)pb->time_scale_lo, (const T*)pb->time_scale_hi, 1};
                 return dispatch<ETile, T>(vec, pb->scheme, ax.z_on, ax.t_on, a);

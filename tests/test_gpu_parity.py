@@ -727,3 +727,85 @@ def test_host_entry_points():
         assert e.value == pytest.approx(s.energy(), rel=1e-12)
     np.testing.assert_array_equal(xo, s.result())
     _lib.check(lib.pytvb_cp_destroy(handle))
+
+
+# ------------------------------------------------------------------ launch-bound volumes: plans, graphs, BASELINE config 1
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_tv_plan_equals_the_drop_in_call(scheme):
+    """TVPlan (pre-allocated buffers, CUDA-graph replay) returns exactly what tv_<scheme> returns, call after call, and the
+    cached-plan path behind the numpy-in / numpy-out call equals the tensor path."""
+    rs = np.random.RandomState(31)
+    kw = dict(reg_z_over_reg=0.7, reg_time=0.3)
+    plan = pytv.TVPlan(scheme, (5, 3, 33, 40), torch.float64, return_grad_norms=True, **kw)
+    for k in range(3):
+        x = rs.rand(5, 3, 33, 40)
+        tv_p, G_p = plan(x)
+        tv_t, G_t, n_t = tv_(scheme)(torch.as_tensor(x).cuda(), return_pytorch_tensor=True, return_grad_norms=True, **kw)
+        assert float(tv_p) == float(tv_t)
+        assert torch.equal(G_p, G_t) and torch.equal(plan.norms, n_t)
+        tv_n, G_n, n_n = tv_(scheme)(x, return_grad_norms=True, **kw)          # numpy in -> cached plan
+        assert float(tv_n) == float(tv_t) and np.array_equal(G_n, G_t.cpu().numpy()) and np.array_equal(n_n, n_t.cpu().numpy())
+    x32 = rs.rand(5, 3, 33, 40).astype(np.float32)
+    tv_n, G_n = tv_(scheme)(x32, **kw)
+    tv_t, G_t = tv_(scheme)(torch.as_tensor(x32).cuda(), return_pytorch_tensor=True, **kw)
+    assert G_n.dtype == np.float32 and float(tv_n) == float(tv_t) and np.array_equal(G_n, G_t.cpu().numpy())
+
+
+def test_gd_denoise_graph_equals_eager(golden_kat):
+    x_true = cases.synthetic_image(64)
+    noisy = x_true + 100 * np.random.RandomState(0).rand(*x_true.shape)
+    xa, la = pytv.gd_denoise(noisy, 25.0, 50, 5e-3, scheme="hybrid", return_losses=True, graph=True)
+    xb, lb = pytv.gd_denoise(noisy, 25.0, 50, 5e-3, scheme="hybrid", return_losses=True, graph=False)
+    assert np.array_equal(xa, xb) and np.array_equal(la, lb)
+    np.testing.assert_allclose(la, golden_kat["gd_synthetic64"]["losses"], rtol=1e-10)
+    with pytest.raises(TypeError):
+        pytv.gd_denoise(noisy, 25.0, 2, 5e-3, no_such_weight=1.0)
+
+
+def _cameraman():
+    import os
+    f = os.path.join(os.path.dirname(__file__), "..", "baseline", "_ref", "pytv", "media", "cameraman.npy")
+    return np.load(f).astype(np.float64) if os.path.exists(f) else None
+
+
+@pytest.mark.skipif(_cameraman() is None, reason="cameraman asset of the reference is not redistributed in this repo (travels in baseline/_ref)")
+@pytest.mark.parametrize("N", [256, 512])
+def test_config1_cameraman_300_iterations(N, golden_kat):
+    """BASELINE config 1 as specified (README.md:107-158): the shipped 256 x 256 cameraman (and its 2x2 replication, 512 x 512),
+    noise 100 rand (seed 0), lambda 25: 300 iterations of sub-gradient descent (step 5e-3) and of the README Chambolle-Pock loop
+    on the GPU against the reference-generated goldens (256) / the oracle (512)."""
+    cam = _cameraman()
+    assert cam.sum() == golden_kat["cameraman_checksum"]["sum"]
+    if N == 512:
+        cam = np.kron(cam, np.ones((2, 2)))
+    cam = cam.reshape(1, 1, N, N)
+    np.random.seed(0)
+    noisy = cam + 100 * np.random.rand(*cam.shape)
+    x, losses = pytv.gd_denoise(noisy, 25.0, 300, 5e-3, scheme="hybrid", return_losses=True)
+    s = pytv.CPSolver(noisy, lam=25.0, scheme="hybrid", variant="readme", tau=1 / 9.0)
+    cp_losses = []
+    for _ in range(300):
+        s.step()
+        cp_losses.append(s.energy())
+    if N == 256:
+        g = golden_kat["gd_cameraman"]
+        assert losses[0] == pytest.approx(g["loss_first"], rel=1e-12)
+        assert losses[-1] == pytest.approx(g["loss_last"], rel=1e-5)       # chaotic trajectory: see tests/test_oracle_golden.py
+        c = golden_kat["cp_readme_cameraman"]
+        assert cp_losses[0] == pytest.approx(c["loss_first"], rel=1e-12)
+        assert cp_losses[-1] == pytest.approx(c["loss_last"], rel=1e-11)
+        assert s.result().sum() == pytest.approx(c["sum_x"], rel=1e-12)
+    else:
+        xo = noisy.copy()
+        for it in range(300):
+            tv, G = orc.tv(xo, "hybrid")
+            xo += -5e-3 * ((xo - noisy) + 25.0 * G)
+            loss = 0.5 * np.sum(np.square(xo - noisy)) + 25.0 * tv
+            if it < 40:
+                assert losses[it] == pytest.approx(loss, rel=1e-11)
+        assert losses[-1] == pytest.approx(loss, rel=1e-5)
+        xr, y_f, y_tv = noisy.copy(), np.zeros_like(noisy), np.zeros((1, 4, 1, N, N))
+        for it in range(300):
+            xr, y_f, y_tv, loss = orc.cp_readme_step(xr, noisy, y_f, y_tv, "hybrid", lam=25.0)
+        assert cp_losses[-1] == pytest.approx(loss, rel=1e-11)
+    assert losses[-1] < 0.45 * losses[0] and cp_losses[-1] < losses[-1]        # README.md:126-162: CP converges faster than GD
