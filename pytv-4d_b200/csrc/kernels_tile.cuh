@@ -85,7 +85,7 @@ template <typename T, int VEC>
 PYTVB_HD TileCtx<T> tile_ctx(const TileGeom& g, long long b, const Params<T>& P, unsigned char* smem, bool mask) {
     TileCtx<T> c;
     const int Nz = P.Nz;
-    smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem) + 127) & ~uintptr_t(127));
+    smem += (128 - (int)(reinterpret_cast<uintptr_t>(smem) & 127)) & 127;     // pointer + offset: the compiler keeps the shared address space
     const int tj = (int)(b % g.ntj); b /= g.ntj;
     const int ti = (int)(b % g.nti); b /= g.nti;
     const int fg = (int)(b % g.nfg); b /= g.nfg;

@@ -401,13 +401,15 @@ template <typename T, int VEC, int N>
 PYTVB_HD void quad_sides(T* l, T* r, const T* q, const T* row, int lane, bool edge) {
 #pragma unroll
     for (int k = 0; k < N; ++k) {
+        const int dl = k / VEC + 1, ix = k % VEC;       // element -1-k is element VEC-1-ix of the quad dl lanes to the left
 #if defined(__CUDA_ARCH__)
-        const T sl = __shfl_up_sync(0xffffffffu, q[VEC - 1 - k], 1), sr = __shfl_down_sync(0xffffffffu, q[k], 1);
+        const T sl = __shfl_up_sync(0xffffffffu, q[VEC - 1 - ix], dl), sr = __shfl_down_sync(0xffffffffu, q[ix], dl);
 #else
-        const T sl = lane > 0 ? row[-1 - k] : T(0), sr = lane < 31 ? row[VEC + k] : T(0);
+        const T sl = lane >= dl ? row[-1 - k] : T(0), sr = lane + dl <= 31 ? row[VEC + k] : T(0);
 #endif
-        l[k] = lane > 0 ? sl : ((edge && k == 0) ? row[-1] : q[0]);
-        r[k] = lane < 31 ? sr : ((edge && k == 0) ? row[VEC] : q[VEC - 1]);
+        // lanes without that neighbour: the window has the element when it is not further out than the scalar halo column
+        l[k] = lane >= dl ? sl : ((edge && lane * VEC >= k) ? row[-1 - k] : q[0]);
+        r[k] = lane + dl <= 31 ? sr : ((edge && (31 - lane) * VEC >= k) ? row[VEC + k] : q[VEC - 1]);
     }
 }
 
