@@ -153,7 +153,7 @@ struct TileStager {
     }
 };
 
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, int TSMODE>
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, int TSMODE, bool NORMS>
 __global__ void __launch_bounds__(TILE_MAX_THREADS, PYTVB_TILE_MINB)
 tv_tile_kernel(ImgView<T> X, ImgView<T> TS, T* __restrict__ G, T* __restrict__ norms, double* __restrict__ partial, Params<T> P, TileGeom g,
                const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapLo, const __grid_constant__ CUtensorMap mapHi) {
@@ -181,7 +181,7 @@ tv_tile_kernel(ImgView<T> X, ImgView<T> TS, T* __restrict__ G, T* __restrict__ n
         for (int p = p0; p <= p1; ++p) {
             const bool more = p + 2 <= p1 + 1;
             if (more) sg.issue(p + 2);
-            tile_phase_w<T, VEC, SCHEME, Z_ON, T_ON, R, TSMODE>(st, c, g, P, TS, G, norms, p, tp);
+            tile_phase_w<T, VEC, SCHEME, Z_ON, T_ON, R, TSMODE, NORMS>(st, c, g, P, TS, G, norms, p, tp);
             __syncthreads();
             if (p >= c.zc0 && p < c.zc1) tile_phase_g<T, VEC, SCHEME, Z_ON, T_ON, R, TSMODE>(st, c, g, P, TS, G, p, tp);
             if (more) sg.land(p + 2);
@@ -198,7 +198,7 @@ tv_tile_kernel(ImgView<T> X, ImgView<T> TS, T* __restrict__ G, T* __restrict__ n
         for (int p = c.zc0; p < c.zc1; ++p) {
             const bool more = p + 1 < c.zc1;
             if (more) sg.issue(p + 1);
-            tile_phase_w<T, VEC, SCHEME, Z_ON, T_ON, R, TSMODE>(st, c, g, P, TS, G, norms, p, tp);
+            tile_phase_w<T, VEC, SCHEME, Z_ON, T_ON, R, TSMODE, NORMS>(st, c, g, P, TS, G, norms, p, tp);
             __syncthreads();
             tile_phase_g<T, VEC, SCHEME, Z_ON, T_ON, R, TSMODE>(st, c, g, P, TS, G, p, tp);
             if (more) sg.land(p + 1);

@@ -134,7 +134,7 @@ template <typename T, int VEC, int R>
 struct TileThread {
     T a[R][VEC];    // one-sided / hybrid: raw z difference x(p) - x(p-1);  centred: x(p-1)
     T w[R][VEC];    // w of the plane of the last w-phase
-    T e[R][VEC];    // centred only: srz * Cz(p-1)
+    T e[R][VEC];    // one-sided / hybrid: srz * term(p-1 -> p) of the last w-phase (the z term coming into plane p);  centred: srz * Cz(p-1)
     T g[R][VEC];    // running sub-gradient: in-plane + time part of the last G-phase plus the incoming z term
     double tv;      // running sum of the norms of this thread's output voxels (one double add per step: the float part spans R rows only,
                     // so the value does not depend on how the volume is cut into z chunks or slabs beyond 1e-16)
@@ -301,19 +301,37 @@ PYTVB_HD void tile_stage_mask(const TileCtx<T>& c, const TileGeom& g, const Para
 struct TilePos {
     int fl, rr0, cj;     // frame within the CTA, first work row (tile coordinates, >= -1), tile column of the quad
     int t;               // global frame
+    int lane;            // index of the quad in its work row (0 and 31 are the halo lanes)
     bool col_out;        // the quad lies in the output tile and inside the image
+    int xo, wo;          // element offset of the quad in work row 0 inside an x slot / the w window (frame included)
+    int dxm, dxp;        // element distance to the same quad of the previous / next frame in an x slot (0 at the ends: clamped)
+    int dwm, dwp;        // the same in the w window
     long long goff;      // element offset of (frame t, row i0 + rr0, column j0 + cj) inside a z-plane group (outputs)
 };
-// Computed once per thread (the division by the strip count and the 64-bit products stay out of the z loop).
+// Computed once per thread (the division by the strip count and the 64-bit products stay out of the z loop).  On the device
+// the warp index is read through a shuffle: the compiler then knows that everything derived from it (frame, rows, the row
+// predicates) is warp-uniform and keeps it in uniform registers / uniform branches.
 template <typename T, int VEC, int R>
 PYTVB_HD TilePos tile_pos(const TileCtx<T>& c, const TileGeom& g, const Params<T>& P, int tid) {
     TilePos p;
-    const int lane = tid & 31, wid = tid >> 5;
+    const int lane = tid & 31;
+#if defined(__CUDA_ARCH__)
+    const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
+#else
+    const int wid = tid >> 5;
+#endif
     p.fl = wid / g.strips;
     p.rr0 = -1 + (wid - p.fl * g.strips) * R;
     p.cj = -VEC + lane * VEC;
+    p.lane = lane;
     p.t = c.t0 + p.fl;
     p.col_out = p.cj >= 0 && p.cj < g.TJ && c.j0 + p.cj < P.Nj;     // vector path: Nj % VEC == 0, so a quad is in or out as a whole
+    p.xo = p.fl * g.slotX + (p.rr0 + 2) * TileC<VEC>::PX + p.cj + 2 * VEC;
+    p.wo = p.fl * g.slotW + (p.rr0 + 1) * TileC<VEC>::WJ + p.cj + VEC;
+    p.dxm = p.fl > 0 ? -g.slotX : 0;
+    p.dxp = p.fl < g.FC - 1 ? g.slotX : 0;
+    p.dwm = p.fl > 0 ? -g.slotW : 0;
+    p.dwp = p.fl < g.FC - 1 ? g.slotW : 0;
     p.goff = (long long)p.t * P.sT + (long long)(c.i0 + p.rr0) * P.Nj + c.j0 + p.cj;
     return p;
 }
@@ -352,20 +370,32 @@ PYTVB_HD void tile_time_scale(T* f, const TileCtx<T>& c, const Params<T>& P, con
 template <typename T>
 PYTVB_HD T cen_exists(long long k, long long L) { return (k >= 1 && k <= L - 2) ? T(1) : T(0); }
 
-// w = 1/|D x| (0 where the norm is 0) from the sum of squares: one MUFU, one select.
-template <typename T>
+// w = 1/|D x| from the sum of squares s.  The reference sets 0/0 := 0 (tv_GPU.py:87-88: the norm 0 becomes inf before the
+// division).  Every product the sub-gradient forms with w(v) has a difference that is one of the terms of s(v) as its other
+// factor - the edge terms (x_b - x_a) S(w_a, w_b) pair each w with a difference of its own voxel, the centred C(m) likewise -
+// so where s = 0 that factor is exactly 0 and ANY FINITE w gives the reference's 0.  EXACT = false (the kernel's fast path)
+// therefore skips the select: float on the device is max + MUFU.RSQ + one multiply (a sum of squares below FLT_MIN - all
+// differences < 1.1e-19 - is raised to FLT_MIN, which keeps w finite).  EXACT = true also reports s > 0 (the norms output
+// needs the inf) and returns w = 0 there.
+template <typename T, bool EXACT>
 PYTVB_HD void tile_norm(T s, const Params<T>& P, T& w, bool& pos) {
-    const T rs = fast_rsqrt(s);
     pos = s > T(0);
-    w = pos ? rs * P.div : T(0);
+    w = pos ? fast_rsqrt(s) * P.div : T(0);
 }
 #if defined(__CUDA_ARCH__)
 template <>
-__device__ __forceinline__ void tile_norm<float>(float s, const Params<float>& P, float& w, bool& pos) {
-    float rs;     // a sum of squares below FLT_MIN (all differences < 1.1e-19) counts as zero, as in norm_finish
+__device__ __forceinline__ void tile_norm<float, true>(float s, const Params<float>& P, float& w, bool& pos) {
+    float rs;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(fmaxf(s, 1.17549435e-38f)));
     pos = s >= 1.17549435e-38f;
     w = pos ? rs * P.div : 0.0f;
+}
+template <>
+__device__ __forceinline__ void tile_norm<float, false>(float s, const Params<float>& P, float& w, bool& pos) {
+    float rs;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(fmaxf(s, 1.17549435e-38f)));
+    pos = true;
+    w = rs * P.div;
 }
 #endif
 
@@ -425,25 +455,28 @@ PYTVB_HD void vpair_w(T* d, const T* wk, const T* wk1) {
 
 // ---- w-phase of plane p.  Outputs: w(p) to shared memory, norms (optional) and the TV partial sum for output voxels, and -
 // with the z axis on - the finished G(p-1).
-// Register diet (the kernel is instruction-issue bound, 128 registers per thread at 16 warps per SM): the z edge term is
-// folded into the running sub-gradient - st.g holds  Gp(p-1) + srz * term(p-2 -> p-1)  on entry, G(p-1) = st.g - srz * term(p-1 -> p)
-// is stored, and st.g restarts as  srz * term(p-1 -> p)  for the G-phase to add Gp(p) to - so a thread carries three values
-// per voxel (raw z difference, w, running G), the centred scheme four (x(p-1), Cz(p-1), running G; w within the step).
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, int TSMODE>
+// Instruction diet (the kernel is instruction-issue bound: profiles/r02k_tv_tile_tma_ncu_full.txt, 371 instructions per quad of
+// which 157 floating point):
+//   * the loop-carried state is three values per voxel - the raw z difference a, the running sub-gradient g (in-plane + time
+//     part of plane p-1 plus its incoming z term) and, within a step, the z term e = srz * term(p-1 -> p) handed from the
+//     w-phase to the G-phase - and every carried value is assigned exactly once per step by the arithmetic instruction that
+//     produces it (a register-to-register copy per value and step otherwise: 12 MOVs per quad row): a is recomputed from the
+//     rows still in registers, g = e + Gp in the G-phase, and the previous plane's own w comes back from the w window (it is
+//     still there until this phase overwrites it) instead of living in registers across the step;
+//   * no select on the norm (tile_norm, EXACT only for the norms output), the TV sum as two packed FMAs per row with a 0/1
+//     factor instead of a predicate and a scalar sum per row;
+//   * window offsets per thread computed once (TilePos), the hybrid scheme's backward row difference is the forward one of
+//     the row above.
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, int TSMODE, bool NORMS>
 PYTVB_HD void tile_phase_w(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const TileGeom& g, const Params<T>& P, const ImgView<T>& TS,
                            T* G, T* norms, int p, const TilePos& tp) {
     typedef Comp<SCHEME, Z_ON, T_ON> C;
     typedef VOp<T, VEC> V;
     constexpr bool FWD = C::NEED_FWD, BWD = C::NEED_BWD, CEN = SCHEME == CENTRAL;
     constexpr int PX = TileC<VEC>::PX, WJ = TileC<VEC>::WJ;
-    const int sp = tile_slot(p);
-    const int xo = (tp.rr0 + 2) * PX + tp.cj + 2 * VEC;        // own quad in an x window, work row 0
-    const T* Xp = c.Xs + (long long)sp * g.xslot + (long long)tp.fl * g.slotX + xo;
-    const T* Xn = c.Xs + (long long)tile_slot(p + 1) * g.xslot + (long long)tp.fl * g.slotX + xo;
-    const int flm = tp.fl > 0 ? tp.fl - 1 : tp.fl, flp = tp.fl < g.FC - 1 ? tp.fl + 1 : tp.fl;
-    const T* Xtm = c.Xs + (long long)sp * g.xslot + (long long)flm * g.slotX + xo;
-    const T* Xtp = c.Xs + (long long)sp * g.xslot + (long long)flp * g.slotX + xo;
-    T* Wp = c.Ws + (long long)tp.fl * g.slotW + (tp.rr0 + 1) * WJ + tp.cj + VEC;
+    const T* Xp = c.Xs + (long long)tile_slot(p) * g.xslot + tp.xo;            // own quad in the x window of plane p, work row 0
+    const T* Xn = c.Xs + (long long)tile_slot(p + 1) * g.xslot + tp.xo;
+    T* Wp = c.Ws + tp.wo;
     const int t = tp.t;
     const int ql = tile_clamp_plane(P, p);
     const long long zg = P.zg0 + p;
@@ -451,18 +484,21 @@ PYTVB_HD void tile_phase_w(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
     const T rz2 = P.srz * P.srz, rt2 = P.srt * P.srt, k2 = P.inv_div * P.inv_div;
     const T fz = CEN ? cen_exists<T>(zg, P.NzG) : T(1), ft = CEN ? cen_exists<T>(t, P.M) : T(1);
     T* Gq = G + (long long)(p - 1) * P.sZ + tp.goff;            // G(p-1) at the thread's quad, work row 0
-    const int lane = tp.cj / VEC + 1;
-    T tvstep = T(0);
-    T xu[VEC], xc[VEC];
+    const T colf = tp.col_out ? T(1) : T(0);
+    T tvq[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) tvq[e] = T(0);
+    T xu[VEC], xc[VEC], dip[VEC];
     ld_into<T, VEC>(xu, Xp - PX);
     ld_into<T, VEC>(xc, Xp);
+    if (FWD && BWD) V::sub(dip, xc, xu);           // x(rr) - x(rr-1): the backward row difference of row rr
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const int rr = tp.rr0 + r, gi = c.i0 + rr;
         T xd[VEC], s[VEC];
         ld_into<T, VEC>(xd, Xp + (r + 1) * PX);
         T cl, cr;
-        quad_sides<T, VEC, 1>(&cl, &cr, xc, Xp + r * PX, lane, true);
+        quad_sides<T, VEC, 1>(&cl, &cr, xc, Xp + r * PX, tp.lane, true);
         if (!CEN) {
             // column differences: VEC + 1 of them serve the forward and the backward component of the quad
             T djf[VEC], djb[VEC];
@@ -477,8 +513,14 @@ PYTVB_HD void tile_phase_w(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
                 V::fma(s, djf, djf, s);
             }
             if (BWD) {
-                V::sub(di, xc, xu);
-                if (FWD) V::fma(s, di, di, s); else V::mul(s, di, di);
+                if (FWD) {
+                    V::fma(s, dip, dip, s);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) dip[e] = di[e];
+                } else {
+                    V::sub(di, xc, xu);
+                    V::mul(s, di, di);
+                }
                 V::fma(s, djb, djb, s);
             }
         } else {
@@ -494,13 +536,14 @@ PYTVB_HD void tile_phase_w(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
             V::mul(s, di, di);
             V::fma(s, dj, dj, s);
         }
-        T dzf[VEC];       // one-sided / hybrid: x(p+1) - x(p);  centred: x(p+1) - x(p-1), 0 where it does not exist
+        T xn[VEC], dzf[VEC];       // dzf, centred only: x(p+1) - x(p-1), 0 where it does not exist
         if (Z_ON) {
-            T xn[VEC], q[VEC];
+            T q[VEC];
             ld_into<T, VEC>(xn, Xn + r * PX);
             if (!CEN) {
-                V::sub(dzf, xn, xc);
-                if (FWD) V::mul(q, dzf, dzf);
+                T d[VEC];
+                V::sub(d, xn, xc);
+                if (FWD) V::mul(q, d, d);
                 if (BWD) { if (FWD) V::fma(q, st.a[r], st.a[r], q); else V::mul(q, st.a[r], st.a[r]); }
             } else {
                 V::sub(dzf, xn, st.a[r]);
@@ -511,8 +554,8 @@ PYTVB_HD void tile_phase_w(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
         }
         if (T_ON) {
             T xm[VEC], xp[VEC], q[VEC], d[VEC];
-            ld_into<T, VEC>(xm, Xtm + r * PX);
-            ld_into<T, VEC>(xp, Xtp + r * PX);
+            ld_into<T, VEC>(xm, Xp + r * PX + tp.dxm);
+            ld_into<T, VEC>(xp, Xp + r * PX + tp.dxp);
             if (!CEN) {
                 if (FWD) { V::sub(d, xp, xc); V::mul(q, d, d); }
                 if (BWD) { V::sub(d, xc, xm); if (FWD) V::fma(q, d, d, q); else V::mul(q, d, d); }
@@ -535,37 +578,34 @@ PYTVB_HD void tile_phase_w(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
         T nrv[VEC];
         bool posv[VEC];
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) tile_norm<T>(s[e], P, wq.v[e], posv[e]);
-        V::mul(nrv, s, wq.v);             // |D x| = sqrt(s) / div = s * w / div^2, 0 by itself where w was forced to 0
-        V::muls(nrv, nrv, k2);
-        T rowsum = T(0);
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) rowsum += nrv[e];
-        st_pack<T, VEC>(Wp + r * WJ, wq);
+        for (int e = 0; e < VEC; ++e) tile_norm<T, NORMS>(s[e], P, wq.v[e], posv[e]);
+        V::mul(nrv, s, wq.v);             // |D x| div^2 = sqrt(s) div = s * w (0 by itself where s = 0); scaled by k2 = 1 / div^2 below
         const bool row_out = rr >= 0 && rr < g.TI && gi < P.Ni;        // warp-uniform
-        if (plane_out && row_out && tp.col_out) {
-            tvstep += rowsum;
-            if (norms) {
+        V::fmas(tvq, nrv, row_out ? colf : T(0), tvq);
+        T wold[VEC];                      // this thread's w(p-1): still in the w window until the store below
+        if (Z_ON && !CEN && FWD) ld_into<T, VEC>(wold, Wp + r * WJ);
+        st_pack<T, VEC>(Wp + r * WJ, wq);
+        if constexpr (NORMS) {
+            if (plane_out && row_out && tp.col_out) {
                 Pack<T, VEC> nq;
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) nq.v[e] = posv[e] ? nrv[e] : T(INFINITY);
+                for (int e = 0; e < VEC; ++e) nq.v[e] = posv[e] ? nrv[e] * k2 : T(INFINITY);
                 st_pack<T, VEC>(norms + (long long)p * P.sZ + tp.goff + (long long)r * P.Nj, nq);
             }
         }
         if (Z_ON) {
             // z edge term between planes p-1 and p (centred: Cz(p)); it completes G(p-1)
             Pack<T, VEC> gq;
-            T en[VEC];
             if (!CEN) {
                 T sw[VEC];
-                vpair_w<T, VEC, SCHEME>(sw, st.w[r], wq.v);
-                V::mul(en, st.a[r], sw);
-                V::muls(en, en, P.srz);
-                V::sub(gq.v, st.g[r], en);
+                vpair_w<T, VEC, SCHEME>(sw, wold, wq.v);
+                V::mul(sw, st.a[r], sw);
+                V::muls(st.e[r], sw, P.srz);
+                V::sub(gq.v, st.g[r], st.e[r]);
                 V::muls(gq.v, gq.v, k2);
-#pragma unroll
-                for (int e = 0; e < VEC; ++e) { st.g[r][e] = en[e]; st.a[r][e] = dzf[e]; }
+                V::sub(st.a[r], xn, xc);
             } else {
+                T en[VEC];
                 V::mul(en, dzf, wq.v);
                 V::muls(en, en, P.srz);
                 V::sub(gq.v, st.g[r], en);
@@ -582,24 +622,28 @@ PYTVB_HD void tile_phase_w(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
 #pragma unroll
         for (int e = 0; e < VEC; ++e) { st.w[r][e] = wq.v[e]; xu[e] = xc[e]; xc[e] = xd[e]; }
     }
-    if (plane_out) st.tv += (double)tvstep;
+    if (plane_out) {
+        T sum = tvq[0];
+#pragma unroll
+        for (int e = 1; e < VEC; ++e) sum += tvq[e];
+        st.tv += (double)(sum * k2);
+    }
 }
 
-// ---- G-phase of plane p: in-plane and time edge terms, added to st.g (z axis on) or stored as the finished G(p) (z axis off).
+// ---- G-phase of plane p: in-plane and time edge terms; with the z axis on they start the running sub-gradient of plane p
+// (st.g = st.e + Gp for the one-sided / hybrid schemes, st.g += Gp for the centred one), else they are the finished G(p).
 template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, int TSMODE>
 PYTVB_HD void tile_phase_g(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const TileGeom& g, const Params<T>& P, const ImgView<T>& TS, T* G, int p,
                            const TilePos& tp) {
     typedef VOp<T, VEC> V;
     constexpr bool CEN = SCHEME == CENTRAL;
     constexpr int PX = TileC<VEC>::PX, WJ = TileC<VEC>::WJ;
-    const int sp = tile_slot(p);
-    const int xcol = tp.cj + 2 * VEC, wcol = tp.cj + VEC;
-    const int xo0 = (tp.rr0 + 2) * PX + xcol, wo0 = (tp.rr0 + 1) * WJ + wcol;       // own quad, work row 0
-    const T* Xp = c.Xs + (long long)sp * g.xslot + (long long)tp.fl * g.slotX + xo0;
-    const T* Wp = c.Ws + (long long)tp.fl * g.slotW + wo0;
+    const int wcol = tp.cj + VEC;
+    const T* Xp = c.Xs + (long long)tile_slot(p) * g.xslot + tp.xo;
+    const T* Wp = c.Ws + tp.wo;
     const int t = tp.t;
     const T k2 = P.inv_div * P.inv_div;
-    const int lane = tp.cj / VEC + 1;      // halo lanes (0 and 31) have no outer neighbour in the w window: their results are unused
+    const int lane = tp.lane;              // halo lanes (0 and 31) have no outer neighbour in the w window: their results are unused
     bool have = false;
     T tdn[VEC];          // one-sided / hybrid: row term (rr -> rr+1) of the previous row
     T cu[VEC], cc[VEC];  // centred: C_i(rr-1), C_i(rr)
@@ -705,8 +749,8 @@ PYTVB_HD void tile_phase_g(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
         if (T_ON) {
             const int dm = tp.fl > 0 ? -1 : 0, dp = tp.fl < g.FC - 1 ? 1 : 0;          // neighbouring frames, clamped
             T xm[VEC], xp[VEC], wm[VEC], wp[VEC], wq[VEC], v[VEC], v2[VEC], dx[VEC], sw[VEC];
-            ld_into<T, VEC>(wm, wrow + dm * g.slotW);
-            ld_into<T, VEC>(wp, wrow + dp * g.slotW);
+            ld_into<T, VEC>(wm, wrow + tp.dwm);
+            ld_into<T, VEC>(wp, wrow + tp.dwp);
 #pragma unroll
             for (int e = 0; e < VEC; ++e) wq[e] = wc[e];
             if constexpr (TSMODE == 2) {   // along t the inverse norms travel with their voxel's scale (strip_quad_G_impl)
@@ -719,8 +763,8 @@ PYTVB_HD void tile_phase_g(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
                 V::mul(wp, wp, f);
             }
             if (!CEN) {
-                ld_into<T, VEC>(xm, xrow + dm * g.slotX);
-                ld_into<T, VEC>(xp, xrow + dp * g.slotX);
+                ld_into<T, VEC>(xm, xrow + tp.dxm);
+                ld_into<T, VEC>(xp, xrow + tp.dxp);
                 V::sub(dx, xc, xm);
                 vpair_w<T, VEC, SCHEME>(sw, wm, wq);
                 V::mul(v, dx, sw);
@@ -753,7 +797,8 @@ PYTVB_HD void tile_phase_g(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
             V::add(gq, gq, v);
         }
         if (Z_ON) {
-            V::add(st.g[r], st.g[r], gq);
+            if (!CEN) V::add(st.g[r], st.e[r], gq);
+            else V::add(st.g[r], st.g[r], gq);
         } else {
             if (tp.col_out && gi < P.Ni) {
                 Pack<T, VEC> pk;

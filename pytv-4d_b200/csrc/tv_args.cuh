@@ -12,5 +12,8 @@ template <typename T> struct TvArgs {
 
 // tv_tile.cu
 template <typename T> int run_tv_tile(int vec, int scheme, bool z_on, bool t_on, const TvArgs<T>& a);
+// tv_tile.cu / tv_tile_norms.cu: the kernel sets without / with the norms output
+template <typename T> int run_tv_tile_plain(int vec, int scheme, bool z_on, bool t_on, const TvArgs<T>& a);
+template <typename T> int run_tv_tile_norms(int vec, int scheme, bool z_on, bool t_on, const TvArgs<T>& a);
 
 }  // namespace pytvb

@@ -1,0 +1,4 @@
+// Single-sweep tv_<scheme> kernels with the norms output (return_grad_norms=True, tv_GPU.py:128-131).
+#define PYTVB_TILE_NORMS true
+#define PYTVB_TILE_ENTRY run_tv_tile_norms
+#include "tv_tile_impl.cuh"

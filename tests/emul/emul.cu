@@ -295,7 +295,7 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct ETile {
                     // Emulate the two extremes on alternating steps: before the w-phase / after the G-phase.
                     const bool early = (p & 1) != 0;
                     if (early && p + 2 <= p1 + 1) all([&](int tid) { stage(c, p + 2, tid); });
-                    all([&](int tid) { tile_phase_w<T, VEC, SCHEME, Z, TT, R, TSM>(st[tid], c, g, a.P, a.W, a.out, a.out2, p, tps[tid]); });
+                    all([&](int tid) { if (a.out2) tile_phase_w<T, VEC, SCHEME, Z, TT, R, TSM, true>(st[tid], c, g, a.P, a.W, a.out, a.out2, p, tps[tid]); else tile_phase_w<T, VEC, SCHEME, Z, TT, R, TSM, false>(st[tid], c, g, a.P, a.W, a.out, a.out2, p, tps[tid]); });
                     if (p >= c.zc0 && p < c.zc1) all([&](int tid) { tile_phase_g<T, VEC, SCHEME, Z, TT, R, TSM>(st[tid], c, g, a.P, a.W, a.out, p, tps[tid]); });
                     if (!early && p + 2 <= p1 + 1) all([&](int tid) { stage(c, p + 2, tid); });
                     if (p + 2 <= p1 + 1) all([&](int tid) { land(c, p + 2, tid); });
@@ -306,7 +306,7 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct ETile {
                 for (int p = c.zc0; p < c.zc1; ++p) {
                     const bool early = (p & 1) != 0;
                     if (early && p + 1 < c.zc1) all([&](int tid) { stage(c, p + 1, tid); });
-                    all([&](int tid) { tile_phase_w<T, VEC, SCHEME, Z, TT, R, TSM>(st[tid], c, g, a.P, a.W, a.out, a.out2, p, tps[tid]); });
+                    all([&](int tid) { if (a.out2) tile_phase_w<T, VEC, SCHEME, Z, TT, R, TSM, true>(st[tid], c, g, a.P, a.W, a.out, a.out2, p, tps[tid]); else tile_phase_w<T, VEC, SCHEME, Z, TT, R, TSM, false>(st[tid], c, g, a.P, a.W, a.out, a.out2, p, tps[tid]); });
                     all([&](int tid) { tile_phase_g<T, VEC, SCHEME, Z, TT, R, TSM>(st[tid], c, g, a.P, a.W, a.out, p, tps[tid]); });
                     if (!early && p + 1 < c.zc1) all([&](int tid) { stage(c, p + 1, tid); });
                     if (p + 1 < c.zc1) all([&](int tid) { land(c, p + 1, tid); });
