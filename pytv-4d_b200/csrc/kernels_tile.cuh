@@ -1,8 +1,11 @@
-// Single-sweep tv_<scheme> kernel: z-marching CTA tiles (per-thread code and the design in tile_core.cuh).
+// Single-sweep tv_<scheme> kernels: z-marching CTA tiles.  Two forms share the geometry, the staging and the launch:
+//   form 1 (tile_core.cuh):  per plane a w-phase and a G-phase, two barriers, 3 x slots + 1 w window;
+//   form 2 (tile2_core.cuh): one phase per plane (norms of plane p, sub-gradient of plane p-1), one barrier, 4 x slots + 2 w windows.
 #pragma once
 #include <cuda.h>       // CUtensorMap (type only: the encoder is looked up at run time, tmap.cuh)
 #include "kernels.cuh"
 #include "tile_core.cuh"
+#include "tile2_core.cuh"
 
 #ifndef PYTVB_TILE_R
 #define PYTVB_TILE_R 4          // rows per thread
@@ -24,37 +27,49 @@ constexpr size_t TILE_SMEM_LIMIT = 227 * 1024 - 256;     // opt-in maximum per C
 
 template <typename T>
 inline size_t tile_smem_bytes(const TileGeom& g, bool mask) {
-    size_t b = 128 + ((size_t)3 * g.xslot + (size_t)g.FC * g.slotW) * sizeof(T);      // 128: the windows start on a 128-byte boundary
+    // 128: the windows start on a 128-byte boundary (TMA destination)
+    size_t b = 128 + ((size_t)g.padf + (size_t)g.nslots * g.xslot + (size_t)g.nwbuf * g.wbuf + (size_t)g.padb) * sizeof(T);
     b = (b + 15) & ~size_t(15);
     b += (size_t)g.FC * g.rowsX * (sizeof(long long) + sizeof(int));       // staging tables
     if (mask) b += (size_t)g.RPF * g.WJ;
     return (b + 15) & ~size_t(15);
 }
 
-// Geometry for a problem; returns false when the tile kernel cannot take it (too many coupled frames).
+// The tile of a geometry with `strips` strips per frame (everything that follows from the strip count).
+template <typename T, int R>
+inline void tile_set_strips(TileGeom& g, int strips) {
+    g.strips = strips;
+    g.RPF = strips * R;
+    g.TI = g.RPF - 2;
+    g.rowsX = g.RPF + 2;
+    g.slotX = g.rowsX * g.pitchX;
+    g.slotW = g.RPF * g.WJ;
+    g.xslot = (int)((((size_t)g.FC * g.slotX * sizeof(T) + 127) & ~size_t(127)) / sizeof(T));
+    g.wbuf = g.FC * g.slotW;
+    g.nthreads = 32 * g.FC * g.strips;
+}
+
+// Geometry for a problem in the given form (1 | 2); returns false when the tile kernel cannot take it (too many coupled frames).
 template <typename T, int VEC, int R>
-inline bool make_tile_geom(TileGeom& g, int Nz, int M, int Ni, int Nj, bool t_on, bool mask, int sm_count = 148) {
+inline bool make_tile_geom(TileGeom& g, int Nz, int M, int Ni, int Nj, bool t_on, bool mask, int form = 1, int sm_count = 148) {
     g.FC = t_on ? M : 1;
     g.WJ = 32 * VEC;
     g.TJ = g.WJ - 2 * VEC;
     g.pitchX = g.WJ + 2 * VEC;
+    g.nslots = form == 2 ? 4 : 3;
+    g.nwbuf = form == 2 ? 2 : 1;
+    g.padf = form == 2 ? (int)((((size_t)2 * g.pitchX * sizeof(T) + 127) & ~size_t(127)) / sizeof(T)) : 0;
+    g.padb = form == 2 ? g.WJ : 0;
     if (g.FC * 32 > TILE_MAX_THREADS) return false;
     int strips = PYTVB_TILE_WARPS / g.FC;
     if (strips < 1) strips = 1;
     const int need = (Ni + 2 + R - 1) / R;          // strips that cover the whole image height plus the halo rows
     if (strips > need) strips = need;
     for (;; --strips) {
-        g.strips = strips;
-        g.RPF = strips * R;
-        g.TI = g.RPF - 2;
-        g.rowsX = g.RPF + 2;
-        g.slotX = g.rowsX * g.pitchX;
-        g.slotW = g.RPF * g.WJ;
-        g.xslot = (int)((((size_t)g.FC * g.slotX * sizeof(T) + 127) & ~size_t(127)) / sizeof(T));
+        tile_set_strips<T, R>(g, strips);
         if (tile_smem_bytes<T>(g, mask) <= TILE_SMEM_LIMIT) break;
         if (strips == 1) return false;
     }
-    g.nthreads = 32 * g.FC * g.strips;
     g.nti = (Ni + g.TI - 1) / g.TI;
     g.ntj = (Nj + g.TJ - 1) / g.TJ;
     g.nfg = t_on ? 1 : M;
@@ -80,6 +95,21 @@ inline bool make_tile_geom(TileGeom& g, int Nz, int M, int Ni, int Nj, bool t_on
     return true;
 }
 
+// Which form runs a problem: the one-phase form when it keeps the tile of the two-phase form (its larger shared-memory
+// footprint costs tile rows - redundant norm evaluations - beyond four coupled frames); 0 when neither can take it.
+// force: 1 | 2 = that form if it can take the problem at all.
+template <typename T, int VEC, int R>
+inline int pick_tile_form(TileGeom& g, int Nz, int M, int Ni, int Nj, bool t_on, bool mask, int force = 0) {
+    TileGeom g1, g2;
+    const bool ok1 = make_tile_geom<T, VEC, R>(g1, Nz, M, Ni, Nj, t_on, mask, 1);
+    const bool ok2 = make_tile_geom<T, VEC, R>(g2, Nz, M, Ni, Nj, t_on, mask, 2);
+    if (force == 1 && ok1) { g = g1; return 1; }
+    if (force == 2 && ok2) { g = g2; return 2; }
+    if (ok2 && (!ok1 || g2.strips >= g1.strips)) { g = g2; return 2; }
+    if (ok1) { g = g1; return 1; }
+    return 0;
+}
+
 // Block index -> tile context (j tiles fastest: neighbouring tiles run at the same time and share their halos through L2).
 template <typename T, int VEC>
 PYTVB_HD TileCtx<T> tile_ctx(const TileGeom& g, long long b, const Params<T>& P, unsigned char* smem, bool mask) {
@@ -96,9 +126,9 @@ PYTVB_HD TileCtx<T> tile_ctx(const TileGeom& g, long long b, const Params<T>& P,
     c.zc0 = zc * g.Lz;
     c.zc1 = c.zc0 + g.Lz < Nz ? c.zc0 + g.Lz : Nz;
     c.fix = c.i0 - 2 < 0 || c.i0 - 2 + g.rowsX > P.Ni || c.j0 - 2 * VEC < 0 || c.j0 - 2 * VEC + g.pitchX > P.Nj;
-    c.Xs = reinterpret_cast<T*>(smem);
-    c.Ws = c.Xs + (size_t)3 * g.xslot;
-    size_t off = (((size_t)3 * g.xslot + (size_t)g.FC * g.slotW) * sizeof(T) + 15) & ~size_t(15);
+    c.Xs = reinterpret_cast<T*>(smem) + g.padf;
+    c.Ws = c.Xs + (size_t)g.nslots * g.xslot;
+    size_t off = (((size_t)g.padf + (size_t)g.nslots * g.xslot + (size_t)g.nwbuf * g.wbuf + (size_t)g.padb) * sizeof(T) + 15) & ~size_t(15);
     c.rowg = reinterpret_cast<long long*>(smem + off);
     c.rowd = reinterpret_cast<int*>(c.rowg + (size_t)g.FC * g.rowsX);
     c.Ms = mask ? reinterpret_cast<uint8_t*>(c.rowd + (size_t)g.FC * g.rowsX) : nullptr;
@@ -109,27 +139,27 @@ PYTVB_HD TileCtx<T> tile_ctx(const TileGeom& g, long long b, const Params<T>& P,
 // Staging of one plane of the x window: the vector path (VEC > 1) by TMA - thread 0 issues one box load per plane, everyone
 // waits on the slot's mbarrier and, in CTAs at the image border, repairs the zero-filled cells - the scalar path (row lengths
 // not divisible by the vector width, unaligned pointers: no tensor map possible) by per-thread cp.async with clamped indices.
+// `ql` = slab-local plane (already clamped), `s` = slot of the ring.
 template <typename T, int VEC>
 struct TileStager {
     static constexpr bool TMA = VEC > 1;
     const TileCtx<T>& c; const TileGeom& g; const ImgView<T>& X; const Params<T>& P;
     const CUtensorMap* mapX; const CUtensorMap* mapLo; const CUtensorMap* mapHi;
-    unsigned long long* bar;      // [3], one per slot
+    unsigned long long* bar;      // one per slot
     unsigned parity;              // bit s: parity of the next completion of slot s
     int tid;
     __device__ __forceinline__ void init() {
         parity = 0;
         if (TMA) {
             if (tid == 0) {
-                for (int s = 0; s < 3; ++s) mbar_init(bar + s, 1);
+                for (int s = 0; s < g.nslots; ++s) mbar_init(bar + s, 1);
                 mbar_init_fence();
             }
         }
     }
-    __device__ __forceinline__ void issue(int q) {
+    __device__ __forceinline__ void issue(int ql, int s) {
         if constexpr (TMA) {
             if (tid == 0) {
-                const int s = tile_slot(q), ql = tile_clamp_plane(P, q);
                 const CUtensorMap* m = ql < 0 ? mapLo : (ql >= P.Nz ? mapHi : mapX);
                 const int zi = ql < 0 ? ql + X.depth : (ql >= P.Nz ? ql - P.Nz : ql);
                 fence_proxy_async();
@@ -137,28 +167,43 @@ struct TileStager {
                 tma_load_4d(c.Xs + (size_t)s * g.xslot, m, bar + s, c.j0 - 2 * VEC, c.i0 - 2, c.t0, zi);
             }
         } else {
-            tile_stage_plane<T, VEC>(c, g, X, P, q, tid);
+            tile_stage_plane<T, VEC>(c, g, X, P, ql, s, tid);
         }
     }
-    // plane q has landed (and is repaired); a __syncthreads must follow before other threads' cells are read
-    __device__ __forceinline__ void land(int q) {
+    // the plane of slot s has landed (and is repaired); a __syncthreads must follow before other threads' cells are read
+    __device__ __forceinline__ void land(int s) {
         if constexpr (TMA) {
-            const int s = tile_slot(q);
             mbar_wait(bar + s, (parity >> s) & 1u);
             parity ^= 1u << s;
-            if (c.fix) tile_fixup_plane<T, VEC>(c, g, P, q, tid);
+            if (c.fix) tile_fixup_plane<T, VEC>(c, g, P, s, tid);
         } else {
             stage_wait_all();
         }
     }
 };
 
+// CTA-wide sum of the threads' TV partials -> partial[blockIdx.x]
+__device__ __forceinline__ void tile_store_partial(double v, double* __restrict__ partial, int nthreads) {
+    __shared__ double warp_part[TILE_MAX_THREADS / 32];
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0) warp_part[tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (nthreads >> 5); ++w) s += warp_part[w];
+        partial[blockIdx.x] = s;
+    }
+}
+
+// ---- form 1: two phases per plane
 template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, int TSMODE, bool NORMS>
 __global__ void __launch_bounds__(TILE_MAX_THREADS, PYTVB_TILE_MINB)
 tv_tile_kernel(ImgView<T> X, ImgView<T> TS, T* __restrict__ G, T* __restrict__ norms, double* __restrict__ partial, Params<T> P, TileGeom g,
                const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapLo, const __grid_constant__ CUtensorMap mapHi) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
-    __shared__ __align__(8) unsigned long long stage_bar[3];
+    __shared__ __align__(8) unsigned long long stage_bar[4];
     const int tid = threadIdx.x;
     const bool mask = TSMODE >= 1 && P.mask_static != nullptr;
     const TileCtx<T> c = tile_ctx<T, VEC>(g, blockIdx.x, P, tile_smem, mask);
@@ -172,24 +217,24 @@ tv_tile_kernel(ImgView<T> X, ImgView<T> TS, T* __restrict__ G, T* __restrict__ n
     __syncthreads();
     if (Z_ON) {
         const int p0 = c.zc0 - 1, p1 = c.zc1;
-        sg.issue(p0);
-        sg.issue(p0 + 1);
-        sg.land(p0);
-        sg.land(p0 + 1);
+        sg.issue(tile_clamp_plane(P, p0), tile_slot(p0));
+        sg.issue(tile_clamp_plane(P, p0 + 1), tile_slot(p0 + 1));
+        sg.land(tile_slot(p0));
+        sg.land(tile_slot(p0 + 1));
         __syncthreads();
         tile_init_z<T, VEC, SCHEME, R>(st, c, g, X, P, p0, tp);
         for (int p = p0; p <= p1; ++p) {
             const bool more = p + 2 <= p1 + 1;
-            if (more) sg.issue(p + 2);
+            if (more) sg.issue(tile_clamp_plane(P, p + 2), tile_slot(p + 2));
             tile_phase_w<T, VEC, SCHEME, Z_ON, T_ON, R, TSMODE, NORMS>(st, c, g, P, TS, G, norms, p, tp);
             __syncthreads();
             if (p >= c.zc0 && p < c.zc1) tile_phase_g<T, VEC, SCHEME, Z_ON, T_ON, R, TSMODE>(st, c, g, P, TS, G, p, tp);
-            if (more) sg.land(p + 2);
+            if (more) sg.land(tile_slot(p + 2));
             __syncthreads();
         }
     } else {
-        sg.issue(c.zc0);
-        sg.land(c.zc0);
+        sg.issue(c.zc0, tile_slot(c.zc0));
+        sg.land(tile_slot(c.zc0));
         __syncthreads();
 #pragma unroll
         for (int r = 0; r < R; ++r)
@@ -197,26 +242,54 @@ tv_tile_kernel(ImgView<T> X, ImgView<T> TS, T* __restrict__ G, T* __restrict__ n
             for (int e = 0; e < VEC; ++e) st.a[r][e] = st.w[r][e] = st.e[r][e] = st.g[r][e] = T(0);
         for (int p = c.zc0; p < c.zc1; ++p) {
             const bool more = p + 1 < c.zc1;
-            if (more) sg.issue(p + 1);
+            if (more) sg.issue(p + 1, tile_slot(p + 1));
             tile_phase_w<T, VEC, SCHEME, Z_ON, T_ON, R, TSMODE, NORMS>(st, c, g, P, TS, G, norms, p, tp);
             __syncthreads();
             tile_phase_g<T, VEC, SCHEME, Z_ON, T_ON, R, TSMODE>(st, c, g, P, TS, G, p, tp);
-            if (more) sg.land(p + 1);
+            if (more) sg.land(tile_slot(p + 1));
             __syncthreads();
         }
     }
-    // TV partial of this CTA (threads beyond the geometry's count do not exist: blockDim == g.nthreads)
-    __shared__ double warp_part[TILE_MAX_THREADS / 32];
-    double v = st.tv;
+    tile_store_partial(st.tv, partial, g.nthreads);
+}
+
+// ---- form 2: one phase per plane (tile2_core.cuh)
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, int TSMODE, bool NORMS>
+__global__ void __launch_bounds__(TILE_MAX_THREADS, PYTVB_TILE_MINB)
+tv_tile2_kernel(ImgView<T> X, ImgView<T> TS, T* __restrict__ G, T* __restrict__ norms, double* __restrict__ partial, Params<T> P, TileGeom g,
+                const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapLo, const __grid_constant__ CUtensorMap mapHi) {
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    __shared__ __align__(8) unsigned long long stage_bar[4];
+    const int tid = threadIdx.x;
+    const bool mask = TSMODE >= 1 && P.mask_static != nullptr;
+    const TileCtx<T> c = tile_ctx<T, VEC>(g, blockIdx.x, P, tile_smem, mask);
+    TileStager<T, VEC> sg{c, g, X, P, &mapX, &mapLo, &mapHi, stage_bar, 0u, tid};
+    sg.init();
+    Tile2Thread<T, VEC, R> st;
+    st.tv = 0.0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((tid & 31) == 0) warp_part[tid >> 5] = v;
-    __syncthreads();
-    if (tid == 0) {
-        double s = 0.0;
-        for (int w = 0; w < (g.nthreads >> 5); ++w) s += warp_part[w];
-        partial[blockIdx.x] = s;
+    for (int r = 0; r < R; ++r) {
+        st.xl[r] = st.xr[r] = T(0);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) st.f[r][e] = st.f1[r][e] = T(0);
     }
+    if (mask) tile_stage_mask<T, VEC>(c, g, P, tid);
+    if (!TileStager<T, VEC>::TMA) tile_stage_tables<T>(c, g, P, tid);
+    const TilePos tp = tile_pos<T, VEC, R>(c, g, P, tid);
+    __syncthreads();
+    // steps p0 .. p1: step p needs the planes p-1, p and (z axis on) p+1; plane p+2 lands during step p
+    const int p0 = Z_ON ? c.zc0 - 1 : c.zc0, p1 = c.zc1;
+    for (int q = p0 - 1; q <= p0 + 1; ++q) sg.issue(tile2_plane<T, Z_ON>(P, q), tile2_slot(q));
+    for (int q = p0 - 1; q <= p0 + 1; ++q) sg.land(tile2_slot(q));
+    __syncthreads();
+    for (int p = p0; p <= p1; ++p) {
+        const bool more = p + 2 <= p1 + 1;
+        if (more) sg.issue(tile2_plane<T, Z_ON>(P, p + 2), tile2_slot(p + 2));
+        tile2_step<T, VEC, SCHEME, Z_ON, T_ON, R, TSMODE, NORMS>(st, c, g, P, TS, G, norms, p, tp);
+        if (more) sg.land(tile2_slot(p + 2));
+        __syncthreads();
+    }
+    tile_store_partial(st.tv, partial, g.nthreads);
 }
 #endif
 

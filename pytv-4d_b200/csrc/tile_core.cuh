@@ -103,6 +103,10 @@ struct TileGeom {
     int pitchX, rowsX; // x window: rows -2 .. TI+1, columns -VEC-1 .. TJ+VEC  (pitch = WJ + 2 VEC)
     int slotX, slotW;  // elements of one (plane, frame) x window / w window
     int xslot;         // elements from one plane slot of the x window to the next (FC * slotX rounded up to 128 bytes: TMA destination alignment)
+    int nslots, nwbuf; // plane slots of the x window ring / w windows: 3 / 1 two-phase form, 4 / 2 one-phase form (tile2_core.cuh)
+    int wbuf;          // elements of one w window (FC * slotW)
+    int padf, padb;    // elements kept free in front of the x windows / behind the w windows (the one-phase form's halo rows read one
+                       // or two rows outside their window and drop the result)
     int nti, ntj, nfg, nzc, Lz;   // tiles along i, j; frame groups; z chunks and their length
     int nthreads;
     long long nblocks;
@@ -160,6 +164,17 @@ PYTVB_HD void stage_wait_all() {
 #endif
 }
 
+// The compiler otherwise rebuilds an output address from the kernel parameters inside every predicated store (27 instructions
+// per row in profiles/r02m_*): an empty asm makes the pointer an opaque value that has to stay in its two registers.
+template <typename T>
+PYTVB_HD void keep_in_registers(T*& p) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+l"(p));
+#else
+    (void)p;
+#endif
+}
+
 PYTVB_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // Slab-local index of plane q clamped to the GLOBAL volume (planes outside the slab but inside the volume come from the
@@ -187,10 +202,10 @@ PYTVB_HD void tile_stage_tables(const TileCtx<T>& c, const TileGeom& g, const Pa
 // one add and the copy (the first version recomputed frame / row / clamps per copy and spent 40 % of the kernel's
 // instructions here, profiles/r02b_tv_tile_first_ncu_full.txt).
 template <typename T, int VEC>
-PYTVB_HD void tile_stage_plane(const TileCtx<T>& c, const TileGeom& g, const ImgView<T>& X, const Params<T>& P, int q, int tid) {
+PYTVB_HD void tile_stage_plane(const TileCtx<T>& c, const TileGeom& g, const ImgView<T>& X, const Params<T>& P, int ql, int sl, int tid) {
     const int lane = tid & 31, wid = tid >> 5, nwarps = g.nthreads >> 5;
-    const T* plane = X.row(P, tile_clamp_plane(P, q), 0, 0);
-    T* slot = c.Xs + (long long)tile_slot(q) * g.xslot;
+    const T* plane = X.row(P, ql, 0, 0);
+    T* slot = c.Xs + (long long)sl * g.xslot;
     const int cj = -VEC + lane * VEC;                 // tile column of this lane's quad
     const int gj0 = c.j0 + cj;
     const bool vec_ok = VEC > 1 && gj0 >= 0 && gj0 + VEC <= P.Nj;
@@ -218,9 +233,9 @@ PYTVB_HD void tile_stage_plane(const TileCtx<T>& c, const TileGeom& g, const Img
 // every out-of-range cell takes the value of the cell with both indices clamped (always an in-range cell of the same
 // frame and window, so the repair reads only cells TMA wrote and writes only cells it zero-filled: no ordering inside it).
 template <typename T, int VEC>
-PYTVB_HD void tile_fixup_plane(const TileCtx<T>& c, const TileGeom& g, const Params<T>& P, int q, int tid) {
+PYTVB_HD void tile_fixup_plane(const TileCtx<T>& c, const TileGeom& g, const Params<T>& P, int sl, int tid) {
     const int lane = tid & 31, wid = tid >> 5, nwarps = g.nthreads >> 5;
-    T* slot = c.Xs + (long long)tile_slot(q) * g.xslot;
+    T* slot = c.Xs + (long long)sl * g.xslot;
     const int iw = c.i0 - 2, jw = c.j0 - 2 * VEC;           // image row / column of window cell (0, 0)
     const int nrows = g.FC * g.rowsX, nq = g.pitchX / VEC;
     const bool cols_in = jw >= 0 && jw + g.pitchX <= P.Nj;
@@ -243,9 +258,8 @@ PYTVB_HD void tile_fixup_plane(const TileCtx<T>& c, const TileGeom& g, const Par
 
 // What the TMA load leaves in the window, as plain code (host emulation of the vector path: tests/emul).
 template <typename T, int VEC>
-PYTVB_HD void tile_stage_plane_zfill(const TileCtx<T>& c, const TileGeom& g, const ImgView<T>& X, const Params<T>& P, int q, int tid) {
-    T* slot = c.Xs + (long long)tile_slot(q) * g.xslot;
-    const int ql = tile_clamp_plane(P, q);
+PYTVB_HD void tile_stage_plane_zfill(const TileCtx<T>& c, const TileGeom& g, const ImgView<T>& X, const Params<T>& P, int ql, int sl, int tid) {
+    T* slot = c.Xs + (long long)sl * g.xslot;
     const int iw = c.i0 - 2, jw = c.j0 - 2 * VEC;
     const int ncell = g.FC * g.rowsX * g.pitchX;
     for (int k = tid; k < ncell; k += g.nthreads) {
@@ -421,9 +435,10 @@ PYTVB_HD void tile_init_z(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const 
 }
 
 // Elements just left / right of a thread's quad in its row.  A warp covers the 32 consecutive quads of one window row, so
-// on the device they come from the neighbouring lanes' registers (two shuffles); only lanes 0 / 31 read them from the
-// window (`edge` = the window has them: the scalar halo columns of x; not for w, where the halo lanes' results are unused and
-// the quad's own end element stands in).  The scalar loads this replaces had 4-way bank conflicts (lane stride 4 words): 24
+// on the device they come from the neighbouring lanes' registers (two shuffles).  Lanes 0 / 31 have no such neighbour: with
+// `edge` they read the element from the window (the scalar halo columns of x), else the quad's own end element stands in.
+// Only the scalar path (VEC == 1) needs `edge`: of a halo lane's results only the w of the element next to the tile is ever
+// used, and for VEC >= 2 that element's differences stay inside the quad and the tile-side neighbour lane.  The scalar loads this replaces had 4-way bank conflicts (lane stride 4 words): 24
 // of the 64 shared-memory wavefronts per row and warp (profiles/r02f_*).  N elements per side (1, or 2 for the centred
 // column terms): l[0] = element -1, l[1] = element -2; r[0] = element VEC, r[1] = element VEC+1.  `lane` = the quad's index
 // in the row.  The host emulation reads the window where the device shuffles.
@@ -433,13 +448,23 @@ PYTVB_HD void quad_sides(T* l, T* r, const T* q, const T* row, int lane, bool ed
     for (int k = 0; k < N; ++k) {
         const int dl = k / VEC + 1, ix = k % VEC;       // element -1-k is element VEC-1-ix of the quad dl lanes to the left
 #if defined(__CUDA_ARCH__)
-        const T sl = __shfl_up_sync(0xffffffffu, q[VEC - 1 - ix], dl), sr = __shfl_down_sync(0xffffffffu, q[ix], dl);
+        T sl = __shfl_up_sync(0xffffffffu, q[VEC - 1 - ix], dl), sr = __shfl_down_sync(0xffffffffu, q[ix], dl);
 #else
-        const T sl = lane >= dl ? row[-1 - k] : T(0), sr = lane + dl <= 31 ? row[VEC + k] : T(0);
+        T sl = lane >= dl ? row[-1 - k] : T(0), sr = lane + dl <= 31 ? row[VEC + k] : T(0);
 #endif
-        // lanes without that neighbour: the window has the element when it is not further out than the scalar halo column
-        l[k] = lane >= dl ? sl : ((edge && lane * VEC >= k) ? row[-1 - k] : q[0]);
-        r[k] = lane + dl <= 31 ? sr : ((edge && (31 - lane) * VEC >= k) ? row[VEC + k] : q[VEC - 1]);
+        // lanes without that neighbour (written as independent predicated assignments: no branches in the row loop): the window
+        // has the element when it is not further out than the scalar halo column, else the quad's own end element stands in
+        if (edge) {
+            if (lane < dl && lane * VEC >= k) sl = row[-1 - k];
+            if (lane + dl > 31 && (31 - lane) * VEC >= k) sr = row[VEC + k];
+            if (lane < dl && lane * VEC < k) sl = q[0];
+            if (lane + dl > 31 && (31 - lane) * VEC < k) sr = q[VEC - 1];
+        } else {
+            if (lane < dl) sl = q[0];
+            if (lane + dl > 31) sr = q[VEC - 1];
+        }
+        l[k] = sl;
+        r[k] = sr;
     }
 }
 
@@ -484,6 +509,7 @@ PYTVB_HD void tile_phase_w(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
     const T rz2 = P.srz * P.srz, rt2 = P.srt * P.srt, k2 = P.inv_div * P.inv_div;
     const T fz = CEN ? cen_exists<T>(zg, P.NzG) : T(1), ft = CEN ? cen_exists<T>(t, P.M) : T(1);
     T* Gq = G + (long long)(p - 1) * P.sZ + tp.goff;            // G(p-1) at the thread's quad, work row 0
+    keep_in_registers(Gq);
     const T colf = tp.col_out ? T(1) : T(0);
     T tvq[VEC];
 #pragma unroll
@@ -498,7 +524,7 @@ PYTVB_HD void tile_phase_w(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
         T xd[VEC], s[VEC];
         ld_into<T, VEC>(xd, Xp + (r + 1) * PX);
         T cl, cr;
-        quad_sides<T, VEC, 1>(&cl, &cr, xc, Xp + r * PX, tp.lane, true);
+        quad_sides<T, VEC, 1>(&cl, &cr, xc, Xp + r * PX, tp.lane, VEC == 1);
         if (!CEN) {
             // column differences: VEC + 1 of them serve the forward and the backward component of the quad
             T djf[VEC], djb[VEC];
@@ -718,7 +744,7 @@ PYTVB_HD void tile_phase_g(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
         // ---- columns (element-shifted within the quad: scalar code)
         if (!CEN) {
             T xl, xr, wlv, wrv;
-            quad_sides<T, VEC, 1>(&xl, &xr, xc, xrow, lane, true);
+            quad_sides<T, VEC, 1>(&xl, &xr, xc, xrow, lane, VEC == 1);
             quad_sides<T, VEC, 1>(&wlv, &wrv, wc, wrow, lane, false);
             T tj = (xc[0] - xl) * pair_w<T, SCHEME>(wlv, wc[0]);
 #pragma unroll
@@ -734,7 +760,7 @@ PYTVB_HD void tile_phase_g(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
 #pragma unroll
             for (int e = 0; e < VEC; ++e) { xw[e + 2] = xc[e]; ww[e + 1] = wc[e]; }
             T xs_l[2], xs_r[2];
-            quad_sides<T, VEC, 2>(xs_l, xs_r, xc, xrow, lane, true);
+            quad_sides<T, VEC, 2>(xs_l, xs_r, xc, xrow, lane, VEC == 1);
             xw[0] = xs_l[1]; xw[1] = xs_l[0]; xw[VEC + 2] = xs_r[0]; xw[VEC + 3] = xs_r[1];
             quad_sides<T, VEC, 1>(&ww[0], &ww[VEC + 1], wc, wrow, lane, false);
 #pragma unroll

@@ -21,6 +21,13 @@ inline TvPathMode tv_path_mode() {
     return v;
 }
 
+// PYTVB_TILE_FORM = 1 | 2 forces the two-phase / one-phase form of the tile kernel where it can take the problem (A/B
+// measurements); default 0: pick_tile_form chooses.  Read once per process.
+inline int tile_form_forced() {
+    static const int v = [] { const char* e = getenv("PYTVB_TILE_FORM"); return e ? atoi(e) : 0; }();
+    return (v == 1 || v == 2) ? v : 0;
+}
+
 // Can the tile kernel take the problem at all?
 inline bool tv_tile_possible(const pytvb_problem* pb) {
     const Axes ax = axes_of(pb);
@@ -28,8 +35,8 @@ inline bool tv_tile_possible(const pytvb_problem* pb) {
     if (pb->scheme == PYTVB_CENTRAL && ((ax.z_on && pb->Nz_global == 2) || (ax.t_on && pb->M == 2))) return false;
     TileGeom g;
     const bool mask = ax.t_on && pb->mask_static;
-    if (pb->dtype == PYTVB_F32) return make_tile_geom<float, 4, PYTVB_TILE_R>(g, (int)pb->Nz, (int)pb->M, (int)pb->Ni, (int)pb->Nj, ax.t_on, mask);
-    return make_tile_geom<double, 2, PYTVB_TILE_R>(g, (int)pb->Nz, (int)pb->M, (int)pb->Ni, (int)pb->Nj, ax.t_on, mask);
+    if (pb->dtype == PYTVB_F32) return pick_tile_form<float, 4, PYTVB_TILE_R>(g, (int)pb->Nz, (int)pb->M, (int)pb->Ni, (int)pb->Nj, ax.t_on, mask) != 0;
+    return pick_tile_form<double, 2, PYTVB_TILE_R>(g, (int)pb->Nz, (int)pb->M, (int)pb->Ni, (int)pb->Nj, ax.t_on, mask) != 0;
 }
 
 // Which form runs.  Both are parity-green on every golden; the choice is measured speed (profiles/r02g_tv_times.txt,
@@ -56,12 +63,14 @@ inline long long tile_max_blocks(const pytvb_problem* pb) {
     const int Nz = (int)pb->Nz, M = (int)pb->M, Ni = (int)pb->Ni, Nj = (int)pb->Nj;
     TileGeom g;
     long long n = 0;
-    if (pb->dtype == PYTVB_F32) {
-        if (make_tile_geom<float, 4, PYTVB_TILE_R>(g, Nz, M, Ni, Nj, ax.t_on, mask) && g.nblocks > n) n = g.nblocks;
-        if (make_tile_geom<float, 1, PYTVB_TILE_R>(g, Nz, M, Ni, Nj, ax.t_on, mask) && g.nblocks > n) n = g.nblocks;
-    } else {
-        if (make_tile_geom<double, 2, PYTVB_TILE_R>(g, Nz, M, Ni, Nj, ax.t_on, mask) && g.nblocks > n) n = g.nblocks;
-        if (make_tile_geom<double, 1, PYTVB_TILE_R>(g, Nz, M, Ni, Nj, ax.t_on, mask) && g.nblocks > n) n = g.nblocks;
+    for (int form = 1; form <= 2; ++form) {
+        if (pb->dtype == PYTVB_F32) {
+            if (make_tile_geom<float, 4, PYTVB_TILE_R>(g, Nz, M, Ni, Nj, ax.t_on, mask, form) && g.nblocks > n) n = g.nblocks;
+            if (make_tile_geom<float, 1, PYTVB_TILE_R>(g, Nz, M, Ni, Nj, ax.t_on, mask, form) && g.nblocks > n) n = g.nblocks;
+        } else {
+            if (make_tile_geom<double, 2, PYTVB_TILE_R>(g, Nz, M, Ni, Nj, ax.t_on, mask, form) && g.nblocks > n) n = g.nblocks;
+            if (make_tile_geom<double, 1, PYTVB_TILE_R>(g, Nz, M, Ni, Nj, ax.t_on, mask, form) && g.nblocks > n) n = g.nblocks;
+        }
     }
     return n;
 }

@@ -11,9 +11,14 @@ using namespace pytvb;
 namespace {
 
 // ---- single-sweep tile kernel (kernels_tile.cuh): one launch, x read once, G written once
-template <typename T, int VEC, int SCHEME, bool Z, bool TT, int TSMODE>
+template <typename T, int VEC, int SCHEME, bool Z, bool TT, int TSMODE, int FORM>
+auto tile_kernel_ptr() {
+    if constexpr (FORM == 2) return tv_tile2_kernel<T, VEC, SCHEME, Z, TT, PYTVB_TILE_R, TSMODE, PYTVB_TILE_NORMS>;
+    else return tv_tile_kernel<T, VEC, SCHEME, Z, TT, PYTVB_TILE_R, TSMODE, PYTVB_TILE_NORMS>;
+}
+template <typename T, int VEC, int SCHEME, bool Z, bool TT, int TSMODE, int FORM>
 int launch_tile(const TvArgs<T>& a, const TileGeom& g, size_t smem) {
-    auto kern = tv_tile_kernel<T, VEC, SCHEME, Z, TT, PYTVB_TILE_R, TSMODE, PYTVB_TILE_NORMS>;
+    auto kern = tile_kernel_ptr<T, VEC, SCHEME, Z, TT, TSMODE, FORM>();
     static bool attr_set = false;      // per instantiation; the attribute is sticky for the function
     if (!attr_set) {
         PYTVB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_LIMIT));
@@ -38,12 +43,18 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct LaunchTvTile 
     static int run(const TvArgs<T>& a) {
         TileGeom g;
         const bool mask = TT && a.P.mask_static;
-        PYTVB_REQUIRE((make_tile_geom<T, VEC, PYTVB_TILE_R>(g, a.P.Nz, a.P.M, a.P.Ni, a.P.Nj, TT, mask)), "internal: the tile kernel does not take this problem");
+        const int form = pick_tile_form<T, VEC, PYTVB_TILE_R>(g, a.P.Nz, a.P.M, a.P.Ni, a.P.Nj, TT, mask, tile_form_forced());
+        PYTVB_REQUIRE(form != 0, "internal: the tile kernel does not take this problem");
         PYTVB_REQUIRE(g.nblocks > 0 && g.nblocks < 2147483647LL, "grid of %lld CTAs is out of range", g.nblocks);
         const size_t smem = tile_smem_bytes<T>(g, mask);
-        if (TT && a.P.tscale) return launch_tile<T, VEC, SCHEME, Z, TT, TT ? 2 : 0>(a, g, smem);
-        if (mask) return launch_tile<T, VEC, SCHEME, Z, TT, TT ? 1 : 0>(a, g, smem);
-        return launch_tile<T, VEC, SCHEME, Z, TT, 0>(a, g, smem);
+        if (form == 2) {
+            if (TT && a.P.tscale) return launch_tile<T, VEC, SCHEME, Z, TT, TT ? 2 : 0, 2>(a, g, smem);
+            if (mask) return launch_tile<T, VEC, SCHEME, Z, TT, TT ? 1 : 0, 2>(a, g, smem);
+            return launch_tile<T, VEC, SCHEME, Z, TT, 0, 2>(a, g, smem);
+        }
+        if (TT && a.P.tscale) return launch_tile<T, VEC, SCHEME, Z, TT, TT ? 2 : 0, 1>(a, g, smem);
+        if (mask) return launch_tile<T, VEC, SCHEME, Z, TT, TT ? 1 : 0, 1>(a, g, smem);
+        return launch_tile<T, VEC, SCHEME, Z, TT, 0, 1>(a, g, smem);
     }
 };
 

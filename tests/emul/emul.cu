@@ -245,24 +245,68 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct ETV2 {
 
 // Single-sweep tile kernel (kernels_tile.cuh), CTA by CTA; inside a CTA the phases between two barriers are run for all
 // threads one after the other, which is one valid execution of the kernel.
-static int g_tile_strips = 0, g_tile_Lz = 0;      // test overrides of the geometry (0 = what the library chooses)
+static int g_tile_strips = 0, g_tile_Lz = 0, g_tile_form = 0;      // test overrides of the geometry / the form (0 = what the library chooses)
 template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct ETile {
     static int run(const EArgs<T>& a) {
         constexpr int R = PYTVB_TILE_R;
         TileGeom g;
         const bool mask = TT && a.P.mask_static;
-        if (!make_tile_geom<T, VEC, R>(g, a.P.Nz, a.P.M, a.P.Ni, a.P.Nj, TT, mask)) return -20;
+        const int form = pick_tile_form<T, VEC, R>(g, a.P.Nz, a.P.M, a.P.Ni, a.P.Nj, TT, mask, g_tile_form);
+        if (!form) return -20;
         if (g_tile_strips > 0 && g_tile_strips < g.strips) {
-            g.strips = g_tile_strips; g.RPF = g.strips * R; g.TI = g.RPF - 2; g.rowsX = g.RPF + 2; g.slotX = g.rowsX * g.pitchX; g.slotW = g.RPF * g.WJ;
-            g.xslot = (int)((((size_t)g.FC * g.slotX * sizeof(T) + 127) & ~size_t(127)) / sizeof(T));
-            g.nthreads = 32 * g.FC * g.strips; g.nti = (a.P.Ni + g.TI - 1) / g.TI;
+            tile_set_strips<T, R>(g, g_tile_strips);
+            g.nti = (a.P.Ni + g.TI - 1) / g.TI;
             g.nblocks = (long long)g.nti * g.ntj * g.nfg * g.nzc;
         }
         if (g_tile_Lz > 0) { g.Lz = g_tile_Lz; g.nzc = (a.P.Nz + g.Lz - 1) / g.Lz; g.nblocks = (long long)g.nti * g.ntj * g.nfg * g.nzc; }
         const int tsmode = (TT && a.P.tscale) ? 2 : (mask ? 1 : 0);
+        if (form == 2) {
+            if (tsmode == 2) return run_mode2<2>(a, g, mask);
+            if (tsmode == 1) return run_mode2<1>(a, g, mask);
+            return run_mode2<0>(a, g, mask);
+        }
         if (tsmode == 2) return run_mode<2>(a, g, mask);
         if (tsmode == 1) return run_mode<1>(a, g, mask);
         return run_mode<0>(a, g, mask);
+    }
+    // one-phase form (tile2_core.cuh): threads one after the other within a step is a valid execution (a step reads the windows of
+    // the planes p-1, p, p+1 and the w window of plane p-1, and writes only the other w window)
+    template <int TSMODE> static int run_mode2(const EArgs<T>& a, const TileGeom& g, bool mask) {
+        constexpr int R = PYTVB_TILE_R;
+        constexpr int TSM = TT ? TSMODE : 0;
+        std::vector<unsigned char> smem(tile_smem_bytes<T>(g, mask) + 16);
+        auto stage = [&](const TileCtx<T>& c, int q, int tid) {
+            const int ql = tile2_plane<T, Z>(a.P, q), sl = tile2_slot(q);
+            if (VEC > 1) tile_stage_plane_zfill<T, VEC>(c, g, a.X, a.P, ql, sl, tid); else tile_stage_plane<T, VEC>(c, g, a.X, a.P, ql, sl, tid);
+        };
+        auto land = [&](const TileCtx<T>& c, int q, int tid) { if (VEC > 1 && c.fix) tile_fixup_plane<T, VEC>(c, g, a.P, tile2_slot(q), tid); };
+        std::vector<Tile2Thread<T, VEC, R>> st(g.nthreads);
+        double tv = 0;
+        for (long long b = 0; b < g.nblocks; ++b) {
+            std::fill(smem.begin(), smem.end(), (unsigned char)0xFF);      // NaN pattern: an unstaged element shows up in the results
+            const TileCtx<T> c = tile_ctx<T, VEC>(g, b, a.P, smem.data(), mask);
+            for (auto& s : st) memset(&s, 0, sizeof(s));
+            std::vector<TilePos> tps(g.nthreads);
+            for (int tid = 0; tid < g.nthreads; ++tid) tps[tid] = tile_pos<T, VEC, R>(c, g, a.P, tid);
+            auto all = [&](auto f) { for (int tid = 0; tid < g.nthreads; ++tid) f(tid); };
+            if (mask) all([&](int tid) { tile_stage_mask<T, VEC>(c, g, a.P, tid); });
+            all([&](int tid) { tile_stage_tables<T>(c, g, a.P, tid); });
+            const int p0 = Z ? c.zc0 - 1 : c.zc0, p1 = c.zc1;
+            for (int q = p0 - 1; q <= p0 + 1; ++q) { all([&](int tid) { stage(c, q, tid); }); all([&](int tid) { land(c, q, tid); }); }
+            for (int p = p0; p <= p1; ++p) {
+                const bool more = p + 2 <= p1 + 1, early = (p & 1) != 0;      // the asynchronous load lands before or after the step's work
+                if (more && early) all([&](int tid) { stage(c, p + 2, tid); });
+                all([&](int tid) {
+                    if (a.out2) tile2_step<T, VEC, SCHEME, Z, TT, R, TSM, true>(st[tid], c, g, a.P, a.W, a.out, a.out2, p, tps[tid]);
+                    else tile2_step<T, VEC, SCHEME, Z, TT, R, TSM, false>(st[tid], c, g, a.P, a.W, a.out, a.out2, p, tps[tid]);
+                });
+                if (more && !early) all([&](int tid) { stage(c, p + 2, tid); });
+                if (more) all([&](int tid) { land(c, p + 2, tid); });
+            }
+            for (auto& s : st) tv += (double)s.tv;
+        }
+        *a.sum = tv;
+        return 0;
     }
     template <int TSMODE> static int run_mode(const EArgs<T>& a, const TileGeom& g, bool mask) {
         constexpr int R = PYTVB_TILE_R;
@@ -271,9 +315,10 @@ template <typename T, int VEC, int SCHEME, bool Z, bool TT> struct ETile {
         // staging as on the device: the vector path by TMA (zero fill outside the image, then the repair of the border CTAs), the scalar
         // path by clamped per-thread copies
         auto stage = [&](const TileCtx<T>& c, int q, int tid) {
-            if (VEC > 1) tile_stage_plane_zfill<T, VEC>(c, g, a.X, a.P, q, tid); else tile_stage_plane<T, VEC>(c, g, a.X, a.P, q, tid);
+            const int ql = Z ? tile_clamp_plane(a.P, q) : q, sl = tile_slot(q);
+            if (VEC > 1) tile_stage_plane_zfill<T, VEC>(c, g, a.X, a.P, ql, sl, tid); else tile_stage_plane<T, VEC>(c, g, a.X, a.P, ql, sl, tid);
         };
-        auto land = [&](const TileCtx<T>& c, int q, int tid) { if (VEC > 1 && c.fix) tile_fixup_plane<T, VEC>(c, g, a.P, q, tid); };
+        auto land = [&](const TileCtx<T>& c, int q, int tid) { if (VEC > 1 && c.fix) tile_fixup_plane<T, VEC>(c, g, a.P, tile_slot(q), tid); };
         std::vector<TileThread<T, VEC, R>> st(g.nthreads);
         double tv = 0;
         for (long long b = 0; b < g.nblocks; ++b) {
@@ -499,5 +544,5 @@ extern "C" int pytvb_emulate_f16y(int op, const pytvb_problem* pb, const void* i
 }
 
 extern "C" void pytvb_emulate_set_rows(int r) { g_emul_rows = (r == 4) ? 4 : 8; }
-extern "C" void pytvb_emulate_set_tile(int strips, int Lz) { g_tile_strips = strips; g_tile_Lz = Lz; }
+extern "C" void pytvb_emulate_set_tile(int strips, int Lz, int form) { g_tile_strips = strips; g_tile_Lz = Lz; g_tile_form = form; }
 extern "C" const char* pytvb_emulate_error(void) { return g_err; }

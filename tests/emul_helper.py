@@ -17,7 +17,7 @@ from pytv_b200 import _lib  # noqa: E402
 
 def build_emul(force=False):
     src = os.path.join(EMUL_DIR, "emul.cu")
-    deps = [src] + [os.path.join(ROOT, "pytv-4d_b200", "csrc", f) for f in ("core.cuh", "strip_core.cuh", "tile_core.cuh", "kernels.cuh", "kernels2.cuh", "kernels_tile.cuh", "host_common.cuh")] + [os.path.join(EMUL_DIR, "gen1_quad.cuh")]
+    deps = [src] + [os.path.join(ROOT, "pytv-4d_b200", "csrc", f) for f in ("core.cuh", "strip_core.cuh", "tile_core.cuh", "tile2_core.cuh", "kernels.cuh", "kernels2.cuh", "kernels_tile.cuh", "host_common.cuh")] + [os.path.join(EMUL_DIR, "gen1_quad.cuh")]
     if not force and os.path.exists(EMUL_SO) and all(os.path.getmtime(EMUL_SO) >= os.path.getmtime(d) for d in deps):
         return EMUL_SO
     cmd = ["nvcc", "-O1", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "--extended-lambda", "-gencode",
@@ -46,10 +46,10 @@ def set_tv_rows(r):
     emul().pytvb_emulate_set_rows(int(r))
 
 
-def set_tile(strips=0, Lz=0):
-    """Geometry overrides of the emulated tile kernel: strips per frame (smaller tiles -> more CTAs along i) and z-chunk length
-    (0 = what the library chooses)."""
-    emul().pytvb_emulate_set_tile(int(strips), int(Lz))
+def set_tile(strips=0, Lz=0, form=0):
+    """Overrides for the emulated tile kernel: strips per frame (smaller tiles -> more CTAs along i), z-chunk length and form
+    (1 = two phases per plane, tile_core.cuh; 2 = one phase, tile2_core.cuh); 0 = what the library chooses."""
+    emul().pytvb_emulate_set_tile(int(strips), int(Lz), int(form))
 
 
 def _ptr(a):

@@ -11,15 +11,17 @@ from oracle import tv_oracle as orc
 SCHEMES = cases.SCHEMES
 
 
-@pytest.fixture(params=[(1, 8, 0, 0), (2, 8, 0, 0), (2, 4, 0, 0), (3, 8, 0, 0), (3, 8, 1, 4)], ids=["gen1", "gen2", "gen2-r4", "tile", "tile-small"])
+@pytest.fixture(params=[(1, 8, 0, 0, 0), (2, 8, 0, 0, 0), (2, 4, 0, 0, 0), (3, 8, 0, 0, 1), (3, 8, 1, 4, 1), (3, 8, 0, 0, 2), (3, 8, 1, 4, 2)],
+                ids=["gen1", "gen2", "gen2-r4", "tile", "tile-small", "tile2", "tile2-small"])
 def gen(request):
     """The retired generation-1 quad code; the strip code (operators, CP passes, the two-sweep tv fallback with 8 and 4 rows per
     thread); and the strip code with tv through the single-sweep tile kernel - what the library runs - with the geometry the
-    library chooses and with the smallest tiles and 4-plane z chunks (many CTAs, every seam exercised)."""
+    library chooses and with the smallest tiles and 4-plane z chunks (many CTAs, every seam exercised), in both forms of the tile
+    kernel (two phases per plane / one phase)."""
     old = em.GEN
-    em.GEN, rows, strips, Lz = request.param
+    em.GEN, rows, strips, Lz, form = request.param
     em.set_tv_rows(rows)
-    em.set_tile(strips, Lz)
+    em.set_tile(strips, Lz, form)
     yield em.GEN
     em.GEN = old
     em.set_tv_rows(8)
@@ -357,16 +359,18 @@ def test_time_weight_map(scheme, shape, scalar):
         p = rs.randn(*D_o.shape)
         np.testing.assert_allclose(em.D_T(p, scheme, scalar=scalar, **kw), orc.D_T(p, scheme, **kw), atol=1e-13)
         tv_o, G_o, n_o = orc.tv(x.copy(), scheme, return_grad_norms=True, **kw)
-        for g_, strips, Lz in ((2, 0, 0), (3, 0, 0), (3, 1, 4)):          # two-sweep fallback, tile kernel, tile kernel with small tiles
+        # two-sweep fallback, tile kernel (both forms), tile kernel with small tiles
+        for g_, strips, Lz, form in ((2, 0, 0, 0), (3, 0, 0, 1), (3, 1, 4, 1), (3, 0, 0, 2), (3, 1, 4, 2)):
             em.GEN = g_
-            em.set_tile(strips, Lz)
+            em.set_tile(strips, Lz, form)
             tv, G, n = em.tv(x, scheme, scalar=scalar, **kw)
             assert tv == pytest.approx(tv_o, rel=1e-13)
             np.testing.assert_allclose(G, G_o, atol=1e-12)
             np.testing.assert_allclose(n, n_o, atol=1e-13)
         # slabs with z halos (tile kernel): the weight map travels with one halo plane per side (pytvb_problem.time_scale_lo / _hi)
-        if Nz >= 3 and not (scheme == "central" and M == 2):
+        for form in ((1, 2) if Nz >= 3 and not (scheme == "central" and M == 2) else ()):
             em.GEN = 3
+            em.set_tile(0, 0, form)
             tv_sum = 0.0
             for a, b in ((0, 1), (1, Nz)):
                 lo2 = np.full((2, M, Ni, Nj), np.nan)
