@@ -71,7 +71,7 @@ PYTVB_HD void tile2_step(Tile2Thread<T, VEC, R>& st, const TileCtx<T>& c, const 
     const int qg = clampi(p - 1, c.zc0, c.zc1 - 1);                                     // plane of the G part (clamped: steps without output)
     const long long zg = P.zg0 + p;
     const bool plane_out = p >= c.zc0 && p < c.zc1, prev_out = p - 1 >= c.zc0 && p - 1 < c.zc1;
-    const T rz2 = P.srz * P.srz, rt2 = P.srt * P.srt, k2 = P.inv_div * P.inv_div;
+    const T rz2 = P.srz * P.srz, rt2 = P.srt * P.srt;
     const T fz = CEN ? cen_exists<T>(zg, P.NzG) : T(1), ft = CEN ? cen_exists<T>(t, P.M) : T(1);
     T* Gq = G + (long long)(p - 1) * P.sZ + tp.goff;            // G(p-1) at the thread's quad, work row 0
     keep_in_registers(Gq);
@@ -305,14 +305,14 @@ PYTVB_HD void tile2_step(Tile2Thread<T, VEC, R>& st, const TileCtx<T>& c, const 
         bool posv[VEC];
 #pragma unroll
         for (int e = 0; e < VEC; ++e) tile_norm<T, NORMS>(s[e], P, wq.v[e], posv[e]);
-        V::mul(nrv, s, wq.v);             // |D x| div^2 = s * w (0 by itself where s = 0); scaled by k2 = 1 / div^2 below
+        V::mul(nrv, s, wq.v);             // |D x| = sqrt(s) / div = s * w (0 by itself where s = 0)
         V::fmas(tvq, nrv, row_out ? colf : T(0), tvq);
         st_pack<T, VEC>(win.Wn + r * WJ, wq);
         if constexpr (NORMS) {
             if (plane_out && row_out && tp.col_out) {
                 Pack<T, VEC> nq;
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) nq.v[e] = posv[e] ? nrv[e] * k2 : T(INFINITY);
+                for (int e = 0; e < VEC; ++e) nq.v[e] = posv[e] ? nrv[e] : T(INFINITY);
                 st_pack<T, VEC>(norms + (long long)p * P.sZ + tp.goff + (long long)r * P.Nj, nq);
             }
         }
@@ -336,7 +336,8 @@ PYTVB_HD void tile2_step(Tile2Thread<T, VEC, R>& st, const TileCtx<T>& c, const 
                 for (int e = 0; e < VEC; ++e) { st.f[r][e] = st.f1[r][e]; st.f1[r][e] = en[e]; }
             }
         }
-        V::muls(go.v, gq, k2);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) go.v[e] = gq[e];
         if (prev_out && row_out && tp.col_out) st_pack<T, VEC>(Gq + (long long)r * P.Nj, go);
 #pragma unroll
         for (int e = 0; e < VEC; ++e) { xu[e] = xc[e]; xc[e] = xd[e]; wc[e] = wd[e]; yc[e] = yd[e]; }
@@ -349,7 +350,7 @@ PYTVB_HD void tile2_step(Tile2Thread<T, VEC, R>& st, const TileCtx<T>& c, const 
         T sum = tvq[0];
 #pragma unroll
         for (int e = 1; e < VEC; ++e) sum += tvq[e];
-        st.tv += (double)(sum * k2);
+        st.tv += (double)sum;
     }
 }
 

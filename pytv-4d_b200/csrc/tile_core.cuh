@@ -384,7 +384,8 @@ PYTVB_HD void tile_time_scale(T* f, const TileCtx<T>& c, const Params<T>& P, con
 template <typename T>
 PYTVB_HD T cen_exists(long long k, long long L) { return (k >= 1 && k <= L - 2) ? T(1) : T(0); }
 
-// w = 1/|D x| from the sum of squares s.  The reference sets 0/0 := 0 (tv_GPU.py:87-88: the norm 0 becomes inf before the
+// w = 1 / (div^2 |D x|) = rsqrt(s) / div from the sum s of the squared raw differences (|D x| = sqrt(s) / div; div = the scheme's
+// divisor): with the 1 / div^2 of the adjoint folded into w the edge terms sum to G directly, and |D x| = s * w.  The reference sets 0/0 := 0 (tv_GPU.py:87-88: the norm 0 becomes inf before the
 // division).  Every product the sub-gradient forms with w(v) has a difference that is one of the terms of s(v) as its other
 // factor - the edge terms (x_b - x_a) S(w_a, w_b) pair each w with a difference of its own voxel, the centred C(m) likewise -
 // so where s = 0 that factor is exactly 0 and ANY FINITE w gives the reference's 0.  EXACT = false (the kernel's fast path)
@@ -394,7 +395,7 @@ PYTVB_HD T cen_exists(long long k, long long L) { return (k >= 1 && k <= L - 2) 
 template <typename T, bool EXACT>
 PYTVB_HD void tile_norm(T s, const Params<T>& P, T& w, bool& pos) {
     pos = s > T(0);
-    w = pos ? fast_rsqrt(s) * P.div : T(0);
+    w = pos ? fast_rsqrt(s) * P.inv_div : T(0);
 }
 #if defined(__CUDA_ARCH__)
 template <>
@@ -402,14 +403,14 @@ __device__ __forceinline__ void tile_norm<float, true>(float s, const Params<flo
     float rs;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(fmaxf(s, 1.17549435e-38f)));
     pos = s >= 1.17549435e-38f;
-    w = pos ? rs * P.div : 0.0f;
+    w = pos ? rs * P.inv_div : 0.0f;
 }
 template <>
 __device__ __forceinline__ void tile_norm<float, false>(float s, const Params<float>& P, float& w, bool& pos) {
     float rs;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(fmaxf(s, 1.17549435e-38f)));
     pos = true;
-    w = rs * P.div;
+    w = rs * P.inv_div;
 }
 #endif
 
@@ -506,7 +507,7 @@ PYTVB_HD void tile_phase_w(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
     const int ql = tile_clamp_plane(P, p);
     const long long zg = P.zg0 + p;
     const bool plane_out = p >= c.zc0 && p < c.zc1, prev_out = Z_ON && p - 1 >= c.zc0 && p - 1 < c.zc1;
-    const T rz2 = P.srz * P.srz, rt2 = P.srt * P.srt, k2 = P.inv_div * P.inv_div;
+    const T rz2 = P.srz * P.srz, rt2 = P.srt * P.srt;
     const T fz = CEN ? cen_exists<T>(zg, P.NzG) : T(1), ft = CEN ? cen_exists<T>(t, P.M) : T(1);
     T* Gq = G + (long long)(p - 1) * P.sZ + tp.goff;            // G(p-1) at the thread's quad, work row 0
     keep_in_registers(Gq);
@@ -605,7 +606,7 @@ PYTVB_HD void tile_phase_w(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
         bool posv[VEC];
 #pragma unroll
         for (int e = 0; e < VEC; ++e) tile_norm<T, NORMS>(s[e], P, wq.v[e], posv[e]);
-        V::mul(nrv, s, wq.v);             // |D x| div^2 = sqrt(s) div = s * w (0 by itself where s = 0); scaled by k2 = 1 / div^2 below
+        V::mul(nrv, s, wq.v);             // |D x| = sqrt(s) / div = s * w (0 by itself where s = 0)
         const bool row_out = rr >= 0 && rr < g.TI && gi < P.Ni;        // warp-uniform
         V::fmas(tvq, nrv, row_out ? colf : T(0), tvq);
         T wold[VEC];                      // this thread's w(p-1): still in the w window until the store below
@@ -615,7 +616,7 @@ PYTVB_HD void tile_phase_w(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
             if (plane_out && row_out && tp.col_out) {
                 Pack<T, VEC> nq;
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) nq.v[e] = posv[e] ? nrv[e] * k2 : T(INFINITY);
+                for (int e = 0; e < VEC; ++e) nq.v[e] = posv[e] ? nrv[e] : T(INFINITY);
                 st_pack<T, VEC>(norms + (long long)p * P.sZ + tp.goff + (long long)r * P.Nj, nq);
             }
         }
@@ -628,14 +629,12 @@ PYTVB_HD void tile_phase_w(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
                 V::mul(sw, st.a[r], sw);
                 V::muls(st.e[r], sw, P.srz);
                 V::sub(gq.v, st.g[r], st.e[r]);
-                V::muls(gq.v, gq.v, k2);
                 V::sub(st.a[r], xn, xc);
             } else {
                 T en[VEC];
                 V::mul(en, dzf, wq.v);
                 V::muls(en, en, P.srz);
                 V::sub(gq.v, st.g[r], en);
-                V::muls(gq.v, gq.v, k2);
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) {
                     st.g[r][e] = st.e[r][e];        // srz * Cz(p-1): the incoming z term of G(p)
@@ -652,7 +651,7 @@ PYTVB_HD void tile_phase_w(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
         T sum = tvq[0];
 #pragma unroll
         for (int e = 1; e < VEC; ++e) sum += tvq[e];
-        st.tv += (double)(sum * k2);
+        st.tv += (double)sum;
     }
 }
 
@@ -668,7 +667,6 @@ PYTVB_HD void tile_phase_g(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
     const T* Xp = c.Xs + (long long)tile_slot(p) * g.xslot + tp.xo;
     const T* Wp = c.Ws + tp.wo;
     const int t = tp.t;
-    const T k2 = P.inv_div * P.inv_div;
     const int lane = tp.lane;              // halo lanes (0 and 31) have no outer neighbour in the w window: their results are unused
     bool have = false;
     T tdn[VEC];          // one-sided / hybrid: row term (rr -> rr+1) of the previous row
@@ -828,7 +826,8 @@ PYTVB_HD void tile_phase_g(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
         } else {
             if (tp.col_out && gi < P.Ni) {
                 Pack<T, VEC> pk;
-                V::muls(pk.v, gq, k2);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) pk.v[e] = gq[e];
                 st_pack<T, VEC>(G + (long long)p * P.sZ + tp.goff + (long long)r * P.Nj, pk);
             }
         }

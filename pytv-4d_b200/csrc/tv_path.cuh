@@ -39,21 +39,14 @@ inline bool tv_tile_possible(const pytvb_problem* pb) {
     return pick_tile_form<double, 2, PYTVB_TILE_R>(g, (int)pb->Nz, (int)pb->M, (int)pb->Ni, (int)pb->Nj, ax.t_on, mask) != 0;
 }
 
-// Which form runs.  Both are parity-green on every golden; the choice is measured speed (profiles/r02g_tv_times.txt,
-// C4 slab, ms: hybrid 3.13 tile / 2.68 sweeps, upwind 2.78 / 2.29, centred 3.47 / 3.67; 512^3 hybrid 1.00 / 0.64).  The tile kernel
-// moves 1.04 x the algorithmic 8 B/voxel (the sweeps 2.5 x) and needs no workspace, but it is bound by instruction issue at
-// the 16 warps per SM its 126 registers per thread allow, so on large volumes the occupancy of the two sweeps wins for the
-// one-sided and hybrid schemes.  auto: the tile kernel for the centred scheme, for weight maps on slabs with z halos (the
-// sweeps do not take them), and for volumes small enough to be launch-bound (one launch instead of two; no workspace).
+// Which implementation runs.  Both are parity-green on every golden; the choice is measured speed (DESIGN.md 3.3,
+// profiles/r02n_tv_times.txt; C4 slab, ms, tile / sweeps: hybrid 1.96 / 2.68, upwind 1.68 / 2.29, centred 2.23 / 3.67; C5 slab hybrid
+// 7.6 / 11.4; 512^3 hybrid 0.64 / 0.64, upwind 0.56 / 0.62): the tile kernel wherever it can take the problem.  It moves 1.07 x the
+// algorithmic 8 B/voxel (the sweeps 2.5 x), needs no workspace and is one launch.
 inline bool tv_uses_tile(const pytvb_problem* pb) {
     const TvPathMode m = tv_path_mode();
     if (m == TV_SWEEPS || !tv_tile_possible(pb)) return false;
-    if (m == TV_TILE) return true;
-    const Axes ax = axes_of(pb);
-    if (pb->scheme == PYTVB_CENTRAL) return true;
-    if (pb->time_scale && ax.z_on && ax.t_on && (pb->time_scale_lo || pb->time_scale_hi)) return true;
-    const long long V = (long long)pb->Nz * pb->M * pb->Ni * pb->Nj;
-    return V <= (1LL << 20);
+    return true;
 }
 
 // Most CTAs (= TV partial sums) the tile kernel can launch for this problem, over its vector and scalar forms.
