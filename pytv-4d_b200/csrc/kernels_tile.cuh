@@ -73,7 +73,9 @@ inline bool make_tile_geom(TileGeom& g, int Nz, int M, int Ni, int Nj, bool t_on
     g.nti = (Ni + g.TI - 1) / g.TI;
     g.ntj = (Nj + g.TJ - 1) / g.TJ;
     g.nfg = t_on ? 1 : M;
-    // z chunks: enough CTAs to fill the machine in whole waves, against the 2-3 warm-up planes every chunk pays
+    // z chunks: enough CTAs to fill the machine in whole waves, against the 2-3 warm-up planes every chunk pays.  A chunk may be
+    // as short as one plane: a volume with fewer tiles than SMs (the README volume: 8 tiles x 20 planes) is bound by the number of
+    // steps a CTA runs one after the other, not by the redundant warm-up work.
     const long long base = (long long)g.nti * g.ntj * g.nfg;
     size_t occ = TILE_SMEM_LIMIT / tile_smem_bytes<T>(g, mask);
     if (occ * g.nthreads > 2048) occ = 2048 / g.nthreads;
@@ -83,7 +85,6 @@ inline bool make_tile_geom(TileGeom& g, int Nz, int M, int Ni, int Nj, bool t_on
     int best_n = 1;
     for (int n = 1; n <= Nz; ++n) {
         const int L = (Nz + n - 1) / n;
-        if (n > 1 && L < 4) break;
         const long long ctas = base * ((Nz + L - 1) / L);
         const long long waves = (ctas + resident - 1) / resident;
         const long long cost = waves * (L + 3);

@@ -46,26 +46,29 @@ struct Tile2Win {
     const T* Wo;     // w(p-1)
     T* Wn;           // w(p)
 };
-template <typename T>
+// PH >= 0: p & 3 as a compile-time constant (four copies of the step, one per phase of the slot ring; every window is then a
+// loop-invariant offset from two per-thread base addresses) - an experiment, see tile2_step.
+template <typename T, int PH>
 PYTVB_HD Tile2Win<T> tile2_windows(const TileCtx<T>& c, const TileGeom& g, const TilePos& tp, int p) {
+    const int ph = PH >= 0 ? PH : p;        // PH < 0: the phase is taken from the plane index at run time
     Tile2Win<T> w;
-    w.Xm = c.Xs + (long long)tile2_slot(p - 1) * g.xslot + tp.xo;
-    w.Xc = c.Xs + (long long)tile2_slot(p) * g.xslot + tp.xo;
-    w.Xn = c.Xs + (long long)tile2_slot(p + 1) * g.xslot + tp.xo;
-    w.Wo = c.Ws + (long long)((p + 1) & 1) * g.wbuf + tp.wo;
-    w.Wn = c.Ws + (long long)(p & 1) * g.wbuf + tp.wo;
+    w.Xm = c.Xs + (long long)tile2_slot(ph - 1) * g.xslot + tp.xo;
+    w.Xc = c.Xs + (long long)tile2_slot(ph) * g.xslot + tp.xo;
+    w.Xn = c.Xs + (long long)tile2_slot(ph + 1) * g.xslot + tp.xo;
+    w.Wo = c.Ws + (long long)((ph + 1) & 1) * g.wbuf + tp.wo;
+    w.Wn = c.Ws + (long long)(ph & 1) * g.wbuf + tp.wo;
     return w;
 }
 
 // One step: norms of plane p, sub-gradient of plane p-1.
-template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, int TSMODE, bool NORMS>
-PYTVB_HD void tile2_step(Tile2Thread<T, VEC, R>& st, const TileCtx<T>& c, const TileGeom& g, const Params<T>& P, const ImgView<T>& TS, T* G, T* norms, int p,
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, int TSMODE, bool NORMS, int PH>
+PYTVB_HD void tile2_step_ph(Tile2Thread<T, VEC, R>& st, const TileCtx<T>& c, const TileGeom& g, const Params<T>& P, const ImgView<T>& TS, T* G, T* norms, int p,
                          const TilePos& tp) {
     typedef Comp<SCHEME, Z_ON, T_ON> C;
     typedef VOp<T, VEC> V;
     constexpr bool FWD = C::NEED_FWD, BWD = C::NEED_BWD, CEN = SCHEME == CENTRAL;
     constexpr int PX = TileC<VEC>::PX, WJ = TileC<VEC>::WJ;
-    const Tile2Win<T> win = tile2_windows<T>(c, g, tp, p);
+    const Tile2Win<T> win = tile2_windows<T, PH>(c, g, tp, p);
     const int t = tp.t, lane = tp.lane;
     const int ql = tile2_plane<T, Z_ON>(P, p);                                         // plane of the w part
     const int qg = clampi(p - 1, c.zc0, c.zc1 - 1);                                     // plane of the G part (clamped: steps without output)
@@ -352,6 +355,27 @@ PYTVB_HD void tile2_step(Tile2Thread<T, VEC, R>& st, const TileCtx<T>& c, const 
         for (int e = 1; e < VEC; ++e) sum += tvq[e];
         st.tv += (double)sum;
     }
+}
+
+// The step of plane p.  PYTVB_T2_PHASES=1 dispatches on the phase of the slot ring (four copies of the step whose window
+// offsets are loop-invariant: 10 % fewer instructions, but measured SLOWER - 2.38 vs 2.05 ms on the C4 slab,
+// profiles/r02r_tv_times.txt: four times the code and 24 bytes of spills); the default computes the window addresses per step.
+#ifndef PYTVB_T2_PHASES
+#define PYTVB_T2_PHASES 0
+#endif
+template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, int TSMODE, bool NORMS>
+PYTVB_HD void tile2_step(Tile2Thread<T, VEC, R>& st, const TileCtx<T>& c, const TileGeom& g, const Params<T>& P, const ImgView<T>& TS, T* G, T* norms, int p,
+                         const TilePos& tp) {
+#if PYTVB_T2_PHASES
+    switch (p & 3) {
+        case 0: tile2_step_ph<T, VEC, SCHEME, Z_ON, T_ON, R, TSMODE, NORMS, 0>(st, c, g, P, TS, G, norms, p, tp); break;
+        case 1: tile2_step_ph<T, VEC, SCHEME, Z_ON, T_ON, R, TSMODE, NORMS, 1>(st, c, g, P, TS, G, norms, p, tp); break;
+        case 2: tile2_step_ph<T, VEC, SCHEME, Z_ON, T_ON, R, TSMODE, NORMS, 2>(st, c, g, P, TS, G, norms, p, tp); break;
+        default: tile2_step_ph<T, VEC, SCHEME, Z_ON, T_ON, R, TSMODE, NORMS, 3>(st, c, g, P, TS, G, norms, p, tp); break;
+    }
+#else
+    tile2_step_ph<T, VEC, SCHEME, Z_ON, T_ON, R, TSMODE, NORMS, -1>(st, c, g, P, TS, G, norms, p, tp);
+#endif
 }
 
 }  // namespace pytvb

@@ -165,7 +165,9 @@ PYTVB_HD void stage_wait_all() {
 }
 
 // The compiler otherwise rebuilds an output address from the kernel parameters inside every predicated store (27 instructions
-// per row in profiles/r02m_*): an empty asm makes the pointer an opaque value that has to stay in its two registers.
+// per row in profiles/r02m_*): an empty asm makes the pointer an opaque value that has to stay in its two registers.  (The store
+// becomes a generic-address ST; the alternative - the opaque value on the offset, STG kept - costs two registers more and measured
+// slower, profiles/r02r_tv_times.txt.)
 template <typename T>
 PYTVB_HD void keep_in_registers(T*& p) {
 #if defined(__CUDA_ARCH__)
