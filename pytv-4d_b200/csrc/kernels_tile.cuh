@@ -28,7 +28,7 @@ constexpr size_t TILE_SMEM_LIMIT = 227 * 1024 - 256;     // opt-in maximum per C
 template <typename T>
 inline size_t tile_smem_bytes(const TileGeom& g, bool mask) {
     // 128: the windows start on a 128-byte boundary (TMA destination)
-    size_t b = 128 + ((size_t)g.padf + (size_t)g.nslots * g.xslot + (size_t)g.nwbuf * g.wbuf + (size_t)g.padb) * sizeof(T);
+    size_t b = 128 + ((size_t)2 * g.padf + (size_t)g.nslots * g.xslot + (size_t)g.nwbuf * g.wbuf) * sizeof(T);
     b = (b + 15) & ~size_t(15);
     b += (size_t)g.FC * g.rowsX * (sizeof(long long) + sizeof(int));       // staging tables
     if (mask) b += (size_t)g.RPF * g.WJ;
@@ -45,7 +45,7 @@ inline void tile_set_strips(TileGeom& g, int strips) {
     g.slotX = g.rowsX * g.pitchX;
     g.slotW = g.RPF * g.WJ;
     g.xslot = (int)((((size_t)g.FC * g.slotX * sizeof(T) + 127) & ~size_t(127)) / sizeof(T));
-    g.wbuf = g.FC * g.slotW;
+    g.wbuf = g.FC * g.slotW + g.padb;      // form 2: one unused row behind EACH w window (tile2_core.cuh: the halo rows' reads one row outside)
     g.nthreads = 32 * g.FC * g.strips;
 }
 
@@ -128,8 +128,8 @@ PYTVB_HD TileCtx<T> tile_ctx(const TileGeom& g, long long b, const Params<T>& P,
     c.zc1 = c.zc0 + g.Lz < Nz ? c.zc0 + g.Lz : Nz;
     c.fix = c.i0 - 2 < 0 || c.i0 - 2 + g.rowsX > P.Ni || c.j0 - 2 * VEC < 0 || c.j0 - 2 * VEC + g.pitchX > P.Nj;
     c.Xs = reinterpret_cast<T*>(smem) + g.padf;
-    c.Ws = c.Xs + (size_t)g.nslots * g.xslot;
-    size_t off = (((size_t)g.padf + (size_t)g.nslots * g.xslot + (size_t)g.nwbuf * g.wbuf + (size_t)g.padb) * sizeof(T) + 15) & ~size_t(15);
+    c.Ws = c.Xs + (size_t)g.nslots * g.xslot + g.padf;      // padf elements unused on both sides of the x windows
+    size_t off = (((size_t)2 * g.padf + (size_t)g.nslots * g.xslot + (size_t)g.nwbuf * g.wbuf) * sizeof(T) + 15) & ~size_t(15);
     c.rowg = reinterpret_cast<long long*>(smem + off);
     c.rowd = reinterpret_cast<int*>(c.rowg + (size_t)g.FC * g.rowsX);
     c.Ms = mask ? reinterpret_cast<uint8_t*>(c.rowd + (size_t)g.FC * g.rowsX) : nullptr;

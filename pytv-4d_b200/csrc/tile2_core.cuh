@@ -103,8 +103,10 @@ PYTVB_HD void tile2_step_ph(Tile2Thread<T, VEC, R>& st, const TileCtx<T>& c, con
             vpair_w<T, VEC, SCHEME>(sw, wu, wc);
             V::mul(tup, dx, sw);
         } else {
+            // row rr0 - 2 of the window; the first strip (rr0 = -1) would leave the window into the slot that is being staged
+            // (its C_i(-2) only feeds the dropped halo row): it reads row rr0 - 1 instead
             T yu2[VEC];
-            ld_into<T, VEC>(yu2, win.Xm - 2 * PX);
+            ld_into<T, VEC>(yu2, win.Xm - (tp.rr0 >= 0 ? 2 : 1) * PX);
             const int gi0 = c.i0 + tp.rr0;
             V::sub(dx, yc, yu2);
             V::mul(cu, dx, wu);

@@ -104,9 +104,9 @@ struct TileGeom {
     int slotX, slotW;  // elements of one (plane, frame) x window / w window
     int xslot;         // elements from one plane slot of the x window to the next (FC * slotX rounded up to 128 bytes: TMA destination alignment)
     int nslots, nwbuf; // plane slots of the x window ring / w windows: 3 / 1 two-phase form, 4 / 2 one-phase form (tile2_core.cuh)
-    int wbuf;          // elements of one w window (FC * slotW)
-    int padf, padb;    // elements kept free in front of the x windows / behind the w windows (the one-phase form's halo rows read one
-                       // or two rows outside their window and drop the result)
+    int wbuf;          // elements from one w window to the next (FC * slotW + padb)
+    int padf, padb;    // elements kept free in front of and behind the x windows / behind each w window (the one-phase form's halo rows read one
+                       // or two rows outside their window and drop the result; the rows they hit are never written during a step)
     int nti, ntj, nfg, nzc, Lz;   // tiles along i, j; frame groups; z chunks and their length
     int nthreads;
     long long nblocks;
