@@ -144,13 +144,22 @@ int pytvb_apply_mask(const pytvb_problem* pb, void* x, const uint8_t* mask, int 
     if (int rc = check_problem(pb)) return rc;
     PYTVB_REQUIRE(x && mask, "x and mask must not be NULL");
     cudaStream_t st = (cudaStream_t)stream;
-    const long long plane = (long long)pb->Ni * pb->Nj, V = plane * pb->M * pb->Nz;
-    long long nb = (V + CTA_THREADS - 1) / CTA_THREADS;
-    if (nb > 148 * 32) nb = 148 * 32;
-    if (pb->dtype == PYTVB_F32)
-        apply_mask_kernel<float><<<(unsigned)nb, CTA_THREADS, 0, st>>>((float*)x, mask, V, plane, mask_is_plane);
-    else
-        apply_mask_kernel<double><<<(unsigned)nb, CTA_THREADS, 0, st>>>((double*)x, mask, V, plane, mask_is_plane);
+    const long long plane = (long long)pb->Ni * pb->Nj, planes = (long long)pb->M * pb->Nz, V = plane * planes;
+    const size_t es = pb->dtype == PYTVB_F32 ? 4 : 8;
+    const bool quads = pb->Nj % 4 == 0 && reinterpret_cast<uintptr_t>(x) % (4 * es < 16 ? 4 * es : 16) == 0 && reinterpret_cast<uintptr_t>(mask) % 4 == 0;
+    if (quads) {
+        const long long nq = plane / 4;
+        const dim3 grid((unsigned)((nq + CTA_THREADS - 1) / CTA_THREADS), (unsigned)(planes < 64 ? planes : 64));
+        if (pb->dtype == PYTVB_F32) apply_mask_quad_kernel<float><<<grid, CTA_THREADS, 0, st>>>((float*)x, mask, nq, planes, mask_is_plane);
+        else apply_mask_quad_kernel<double><<<grid, CTA_THREADS, 0, st>>>((double*)x, mask, nq, planes, mask_is_plane);
+    } else {
+        long long nb = (V + CTA_THREADS - 1) / CTA_THREADS;
+        if (nb > 148 * 32) nb = 148 * 32;
+        if (pb->dtype == PYTVB_F32)
+            apply_mask_kernel<float><<<(unsigned)nb, CTA_THREADS, 0, st>>>((float*)x, mask, V, plane, mask_is_plane);
+        else
+            apply_mask_kernel<double><<<(unsigned)nb, CTA_THREADS, 0, st>>>((double*)x, mask, V, plane, mask_is_plane);
+    }
     count_launches(1);
     PYTVB_CUDA(cudaGetLastError());
     return PYTVB_OK;

@@ -208,6 +208,24 @@ def test_mask_is_applied_in_place(kind):
     np.testing.assert_allclose(G, G_o, atol=1e-12)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(70, 2, 8, 12), (3, 2, 7, 9), (2, 1, 16, 132)], ids=["140-planes", "odd-width", "wide"])
+@pytest.mark.parametrize("plane", [False, True])
+def test_apply_mask_kernel_forms(dtype, shape, plane):
+    """img[~mask] = 0 (tv_GPU.py:79-80) through both kernels: four pixels per thread walking the planes (row length divisible by 4;
+    more planes than the grid has rows) and the scalar form, full-volume and single-plane masks, NaNs under the mask removed."""
+    rs = np.random.RandomState(5)
+    x = rs.rand(*shape).astype(dtype)
+    mask = (rs.rand(*shape[2:]) > 0.4) if plane else (rs.rand(*shape) > 0.4)
+    full = np.broadcast_to(mask, shape)
+    x[~full] = np.nan
+    xc = torch.as_tensor(x).cuda()
+    getattr(tvG, "tv_upwind")(xc, mask=torch.as_tensor(mask))
+    ref = x.copy()
+    ref[~full] = 0
+    np.testing.assert_array_equal(xc.cpu().numpy(), ref)
+
+
 # ------------------------------------------------------------------ reference test-suite, restated (tests.py)
 @pytest.mark.parametrize("scheme", SCHEMES)
 def test_operator_transpose(scheme):
