@@ -135,9 +135,12 @@ __global__ void __launch_bounds__(CTA_THREADS) DT_strip_kernel(FieldView<T> Pf, 
     });
 }
 
-template <typename T, int VEC, int R>
-__global__ void __launch_bounds__(CTA_THREADS) l21_strip_kernel(const T* __restrict__ D, int Nd, T* __restrict__ norms, double* __restrict__ partial,
+// ND: the number of components as a compile-time constant (the schemes' 2, 3, 4, 6, 8: the loads of a row are then issued together
+// instead of one per trip of a dependent loop - C3 one-sided, Nd = 3: 0.66 of the copy peak in the runtime form), or 0 = runtime.
+template <typename T, int VEC, int R, int ND = 0>
+__global__ void __launch_bounds__(CTA_THREADS) l21_strip_kernel(const T* __restrict__ D, int Nd_rt, T* __restrict__ norms, double* __restrict__ partial,
                                                                 Params<T> P, Tiling tl) {
+    const int Nd = ND > 0 ? ND : Nd_rt;
     const QuadIdx q = decode_quad(tl, (P.Ni + R - 1) / R, VEC);
     T sum = T(0);
     if (q.active) {
@@ -147,10 +150,20 @@ __global__ void __launch_bounds__(CTA_THREADS) l21_strip_kernel(const T* __restr
             T s[VEC];
 #pragma unroll
             for (int e = 0; e < VEC; ++e) s[e] = T(0);
-            for (int k = 0; k < Nd; ++k) {
-                const Pack<T, VEC> v = ld_pack<T, VEC>(base + (long long)k * P.sC + o);
+            if constexpr (ND > 0) {
+                Pack<T, VEC> v[ND];
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) s[e] += v.v[e] * v.v[e];
+                for (int k = 0; k < ND; ++k) v[k] = ld_pack<T, VEC>(base + (long long)k * P.sC + o);
+#pragma unroll
+                for (int k = 0; k < ND; ++k)
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) s[e] += v[k].v[e] * v[k].v[e];
+            } else {
+                for (int k = 0; k < Nd; ++k) {
+                    const Pack<T, VEC> v = ld_pack<T, VEC>(base + (long long)k * P.sC + o);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) s[e] += v.v[e] * v.v[e];
+                }
             }
             Pack<T, VEC> nr;
 #pragma unroll

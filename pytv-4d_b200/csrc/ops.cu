@@ -82,10 +82,20 @@ int run_l21(const pytvb_problem* pb, const void* D, int Nd, void* norms, double*
         constexpr int R = PYTVB_STRIP_R;
         const Tiling tl = make_strip_tiling<R>(P.Nj, P.Ni, P.M, P.Nz, vec);
         if (int rc = check_grid(tl)) return rc;
-        if (vec > 1)
-            l21_strip_kernel<T, VecOf<T>::value, R><<<(unsigned)tl.nblocks, CTA_THREADS, 0, st>>>((const T*)D, Nd, (T*)norms, partial, P, tl);
-        else
+#define PYTVB_L21(ND) l21_strip_kernel<T, VecOf<T>::value, R, ND><<<(unsigned)tl.nblocks, CTA_THREADS, 0, st>>>((const T*)D, Nd, (T*)norms, partial, P, tl)
+        if (vec > 1) {
+            switch (Nd) {       // the schemes' component counts get their own instantiation, any other field the runtime loop
+                case 2: PYTVB_L21(2); break;
+                case 3: PYTVB_L21(3); break;
+                case 4: PYTVB_L21(4); break;
+                case 6: PYTVB_L21(6); break;
+                case 8: PYTVB_L21(8); break;
+                default: PYTVB_L21(0); break;
+            }
+        } else {
             l21_strip_kernel<T, 1, R><<<(unsigned)tl.nblocks, CTA_THREADS, 0, st>>>((const T*)D, Nd, (T*)norms, partial, P, tl);
+        }
+#undef PYTVB_L21
         count_launches(1);
         PYTVB_CUDA(cudaGetLastError());
         return finalize_sum(partial, tl.nblocks, d_sum, st);

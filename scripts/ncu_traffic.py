@@ -33,7 +33,7 @@ def main():
         hdr, units = rows[0], rows[1]
         ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
         for r in rows[2:]:
-            name = re.sub(r"<.*", "", r[ik]).split("::")[-1].split("(")[0].strip()
+            name = re.sub(r"^void\s+", "", re.sub(r"<.*", "", r[ik]).split("::")[-1].split("(")[0].strip())
             b = float(r[ir].replace(",", "")) * UNIT_SCALE[units[ir]] + float(r[iw].replace(",", "")) * UNIT_SCALE[units[iw]]
             acc.setdefault(name, []).append(b)
     doc = {"lib_sha256_16": args.lib_hash.strip(), "reports": [os.path.relpath(r, ROOT) for r in args.reports], "note": args.note,
