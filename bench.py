@@ -258,11 +258,11 @@ def measured_hbm_peak():
 
 
 def lib_build_id():
-    """sha256 (first 16 hex digits) of the CUDA library the run loaded: ties recorded ncu traffic to a build."""
-    import hashlib
+    """Identity of the CUDA library the run loaded: pytvb_build_id(), the hash of the sources it was built from (stable across
+    rebuilds, unlike the bytes of the binary).  Ties recorded ncu traffic to a build."""
     from pytv_b200 import _lib
     try:
-        return hashlib.sha256(open(_lib.LIB_PATH, "rb").read()).hexdigest()[:16]
+        return _lib.lib().pytvb_build_id().decode()
     except Exception:
         return None
 
@@ -275,7 +275,7 @@ def recorded_traffic():
         doc = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
         return {}
-    if doc.get("lib_sha256_16") and doc.get("lib_sha256_16") == lib_build_id():
+    if doc.get("build_id") and doc.get("build_id") == lib_build_id():
         return doc.get("kernels", {})
     return {}
 
@@ -632,7 +632,7 @@ def run_ours(args):
                                "traffic": traffic.get("cp_primal_strip_kernel")},
                     "iteration": {"algorithmic_bytes": dual_bytes + primal_bytes, "achieved": (dual_bytes + primal_bytes) * K / (t_ms * 1e-3) / 1e9,
                                   "frac": (dual_bytes + primal_bytes) * K / (t_ms * 1e-3) / 1e9 / peak},
-                    "lib_sha256_16": lib_build_id()}
+                    "build_id": lib_build_id()}
         e2e_gbps = img_bytes * world / (e2e_s / K) / 1e9
         line = {"metric": w["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_ms / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -781,7 +781,7 @@ def run_c5(args, dev, rank, world, gate, mg_check, barrier):
                 "roofline": {"bound": "hbm", "kernel": "D_strip_kernel (hybrid, Nd=8; the largest share of the step)", "achieved": dom["achieved_GBps"],
                              "peak": peak, "unit": "GB/s", "frac": dom["frac"], "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": dom["bytes_per_voxel"] * V_local, "avg_launch_ms": dom["ms"], "traffic": None,
-                             "lib_sha256_16": lib_build_id()},
+                             "build_id": lib_build_id()},
                 "per_op": per_op,
                 "e2e": {"value": int(np.prod(e2e_shape)) / e2e_s, "unit": "voxels/s", "h2d_bytes_per_step": int(np.prod(e2e_shape)) * 4,
                         "d2h_bytes_per_step": int(np.prod(e2e_shape)) * 4 + 8, "ms_per_step": e2e_s * 1e3,

@@ -59,6 +59,10 @@ typedef struct pytvb_problem {
 } pytvb_problem;
 
 int pytvb_version(void);
+/* Identifies the SOURCES the library was built from: the first 16 hex digits of the sha256 over csrc/*.cu, *.cuh and this header (in
+ * sorted order), passed in by the build (Makefile / __graft_entry__.build); "unknown" for any other build.  Ties recorded profiles
+ * (profiles/traffic.json) to a build without depending on the bytes of the binary, which differ from one nvcc run to the next. */
+const char* pytvb_build_id(void);
 const char* pytvb_last_error(void);
 /* Number of CUDA kernels this library has launched in the calling process (diagnostics / benchmarks). */
 uint64_t pytvb_launch_count(void);
@@ -90,9 +94,10 @@ int pytvb_apply_mask(const pytvb_problem* pb, void* x, const uint8_t* mask, int 
 /* tv_<scheme>(img) (tv_GPU.py:47,142,217,290): d_tv[0] = TV (device double), G = the reference's
  * sub-gradient, norms_or_null = gradient norms with inf where zero (return_grad_norms).
  * halo_lo2 / halo_hi2: TWO image planes each (2,M,Ni,Nj): z = -2,-1 and z = Nz, Nz+1.
- * One launch: a z-marching tile kernel reads x once and writes G once (8 bytes per voxel; csrc/tile_core.cuh).  The
- * two-sweep form (inverse norms through a workspace) remains for the cases the tile kernel does not take: more than 16
- * coupled time frames, and the centred scheme on a length-2 z or time axis. */
+ * One launch: a z-marching tile kernel reads x once (TMA into shared-memory windows) and writes G once (8 bytes per voxel;
+ * csrc/tile_core.cuh, tile2_core.cuh).  The two-sweep form (inverse norms through a workspace) remains for the cases the tile
+ * kernel does not take: more than 16 coupled time frames, and the centred scheme on a length-2 z or time axis.
+ * x, G, norms and the halo buffers aligned to 16 bytes and Nj divisible by 4 (float) / 2 (double) select the vector path. */
 int pytvb_tv(const pytvb_problem* pb, const void* x, void* G, void* norms_or_null, double* d_tv, const void* halo_lo2,
              const void* halo_hi2, void* ws_reduce, void* ws_tv, void* stream);
 

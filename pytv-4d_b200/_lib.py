@@ -49,6 +49,7 @@ _VP = ctypes.c_void_p
 _PB = ctypes.POINTER(Problem)
 _PROTOTYPES = {
     "pytvb_version": (ctypes.c_int, []),
+    "pytvb_build_id": (ctypes.c_char_p, []),
     "pytvb_last_error": (ctypes.c_char_p, []),
     "pytvb_launch_count": (ctypes.c_uint64, []),
     "pytvb_num_components": (ctypes.c_int, [_PB]),

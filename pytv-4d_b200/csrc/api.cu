@@ -23,6 +23,10 @@ using namespace pytvb;
 extern "C" {
 
 int pytvb_version(void) { return PYTVB_VERSION; }
+#ifndef PYTVB_SRC_HASH
+#define PYTVB_SRC_HASH "unknown"
+#endif
+const char* pytvb_build_id(void) { return PYTVB_SRC_HASH; }
 const char* pytvb_last_error(void) { return g_err; }
 uint64_t pytvb_launch_count(void) { return (uint64_t)g_launches.load(std::memory_order_relaxed); }
 

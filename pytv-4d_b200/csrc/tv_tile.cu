@@ -1,6 +1,7 @@
-// Single-sweep tv_<scheme> kernels without the norms output (the hot path), and the entry that picks between the two sets.
+// Single-sweep tv_<scheme> kernels without the norms output (the hot path), float; and the entry that picks between the sets.
 #define PYTVB_TILE_NORMS false
 #define PYTVB_TILE_ENTRY run_tv_tile_plain
+#define PYTVB_TILE_T float
 #include "tv_tile_impl.cuh"
 
 namespace pytvb {

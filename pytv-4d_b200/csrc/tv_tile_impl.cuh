@@ -1,5 +1,6 @@
-// tv_<scheme>, single-sweep form: launch of the z-marching tile kernel (kernels_tile.cuh / tile_core.cuh).  Included by tv_tile.cu
-// (kernels without the norms output) and tv_tile_norms.cu (with it): two translation units that compile in parallel.
+// tv_<scheme>, single-sweep form: launch of the z-marching tile kernel (kernels_tile.cuh / tile_core.cuh).  Included by four translation
+// units that compile in parallel (the kernels are the bulk of the library's build time): tv_tile.cu / tv_tile_f64.cu (kernels
+// without the norms output, float / double) and tv_tile_norms.cu / tv_tile_norms_f64.cu (with it).
 #pragma once
 #include "host_common.cuh"
 #include "tv_path.cuh"
@@ -64,6 +65,5 @@ namespace pytvb {
 template <typename T> int PYTVB_TILE_ENTRY(int vec, int scheme, bool z_on, bool t_on, const TvArgs<T>& a) {
     return dispatch<LaunchTvTile, T>(vec, scheme, z_on, t_on, a);
 }
-template int PYTVB_TILE_ENTRY<float>(int, int, bool, bool, const TvArgs<float>&);
-template int PYTVB_TILE_ENTRY<double>(int, int, bool, bool, const TvArgs<double>&);
+template int PYTVB_TILE_ENTRY<PYTVB_TILE_T>(int, int, bool, bool, const TvArgs<PYTVB_TILE_T>&);
 }  // namespace pytvb

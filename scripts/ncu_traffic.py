@@ -36,7 +36,7 @@ def main():
             name = re.sub(r"^void\s+", "", re.sub(r"<.*", "", r[ik]).split("::")[-1].split("(")[0].strip())
             b = float(r[ir].replace(",", "")) * UNIT_SCALE[units[ir]] + float(r[iw].replace(",", "")) * UNIT_SCALE[units[iw]]
             acc.setdefault(name, []).append(b)
-    doc = {"lib_sha256_16": args.lib_hash.strip(), "reports": [os.path.relpath(r, ROOT) for r in args.reports], "note": args.note,
+    doc = {"build_id": args.lib_hash.strip(), "reports": [os.path.relpath(r, ROOT) for r in args.reports], "note": args.note,
            "unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum), mean over the captured launches",
            "kernels": {k: sum(v) / len(v) for k, v in acc.items()}, "launches": {k: len(v) for k, v in acc.items()}}
     json.dump(doc, open(args.out, "w"), indent=1)
