@@ -231,30 +231,33 @@ PYTVB_HD void tile_stage_plane(const TileCtx<T>& c, const TileGeom& g, const Img
 // samples (table look-ups, 64-bit addresses, one LDGSTS per quad; profiles/r02f_tv_tile_sass_mix.txt).  With a tensor map of
 // the (planes, M, Ni, Nj) image one thread issues ONE cp.async.bulk.tensor per plane for the whole (FC, rowsX, pitchX) box
 // and the other threads spend nothing.  TMA fills cells outside the tensor with ZEROS, which is the wrong boundary rule
-// here (core.cuh), so the CTAs whose window reaches outside the image (c.fix) repair the window once it has landed:
-// every out-of-range cell takes the value of the cell with both indices clamped (always an in-range cell of the same
-// frame and window, so the repair reads only cells TMA wrote and writes only cells it zero-filled: no ordering inside it).
+// here (core.cuh), so the CTAs whose window reaches outside the image (c.fix) repair the window once it has landed.  Only the
+// FIRST row / column outside the image needs the clamped value: it makes the difference across the image border exactly 0.
+// Everything further out feeds only the w of ring voxels outside the image, and those w meet nothing but that zero difference
+// (edge terms) or a zero existence factor (centred scheme) - any finite value, so the zeros stay.  (The first version clamped
+// every out-of-range cell: up to 16 quads per row in the last column of tiles, 6 % of the kernel on the C4 slab.)  The repair
+// reads only in-image cells and writes only out-of-image cells, rows and columns disjoint (the corners stay zero): no ordering.
 template <typename T, int VEC>
 PYTVB_HD void tile_fixup_plane(const TileCtx<T>& c, const TileGeom& g, const Params<T>& P, int sl, int tid) {
-    const int lane = tid & 31, wid = tid >> 5, nwarps = g.nthreads >> 5;
     T* slot = c.Xs + (long long)sl * g.xslot;
     const int iw = c.i0 - 2, jw = c.j0 - 2 * VEC;           // image row / column of window cell (0, 0)
-    const int nrows = g.FC * g.rowsX, nq = g.pitchX / VEC;
-    const bool cols_in = jw >= 0 && jw + g.pitchX <= P.Nj;
-    for (int rq = wid; rq < nrows; rq += nwarps) {
-        const int fl = rq / g.rowsX, xr = rq - fl * g.rowsX;
-        const int gi = iw + xr, ci = clampi(gi, 0, P.Ni - 1);
-        if (ci == gi && cols_in) continue;
-        const T* src = slot + (long long)fl * g.slotX + (ci - iw) * g.pitchX;
-        T* dst = slot + (long long)fl * g.slotX + xr * g.pitchX;
-        for (int k = lane; k < nq; k += 32) {
-            const int gj = jw + k * VEC;
-            if (ci == gi && gj >= 0 && gj + VEC <= P.Nj) continue;      // Nj % VEC == 0: a quad is in or out as a whole
-            Pack<T, VEC> v;
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) v.v[e] = src[clampi(gj + e, 0, P.Nj - 1) - jw];
-            st_pack<T, VEC>(dst + k * VEC, v);
-        }
+    const int rT = -iw, rB = P.Ni - 1 - iw, cL = -jw, cR = P.Nj - 1 - jw;      // window row / column of the image's first / last
+    const int nq = g.pitchX / VEC;
+    // rows: the row just above the image <- row 0, the row just below <- the last row (in-image columns)
+    for (int k = tid; k < g.FC * 2 * nq; k += g.nthreads) {
+        const int q = k % nq, rest = k / nq, side = rest & 1, fl = rest >> 1;
+        const int rs = side ? rB : rT, rd = side ? rB + 1 : rT - 1;
+        if (rd < 0 || rd >= g.rowsX || q * VEC < cL || q * VEC + VEC - 1 > cR) continue;
+        T* base = slot + (long long)fl * g.slotX + q * VEC;
+        st_pack<T, VEC>(base + rd * g.pitchX, ld_pack<T, VEC>(base + rs * g.pitchX));
+    }
+    // columns: the cell left of the image <- column 0, the cell right of it <- the last column (in-image rows)
+    for (int k = tid; k < g.FC * g.rowsX * 2; k += g.nthreads) {
+        const int side = k & 1, rq = k >> 1, fl = rq / g.rowsX, xr = rq - fl * g.rowsX;
+        const int cs = side ? cR : cL, cd = side ? cR + 1 : cL - 1;
+        if (cd < 0 || cd >= g.pitchX || xr < rT || xr > rB) continue;
+        T* row = slot + (long long)fl * g.slotX + xr * g.pitchX;
+        row[cd] = row[cs];
     }
 }
 
