@@ -71,7 +71,10 @@ uint64_t pytvb_launch_count(void);
 int pytvb_num_components(const pytvb_problem* pb);
 
 /* Scratch sizes.  `reduce`: needed by every call that produces a scalar; `tv`: needed by pytvb_tv (a few bytes when the
- * single-sweep kernel takes the problem, an (Nz+2)-plane inverse-norm field for the two-sweep fallback). */
+ * single-sweep kernel takes the problem, an (Nz+2)-plane inverse-norm field for the two-sweep fallback).
+ * The reduce workspace must be ZERO-INITIALISED before its first use (cudaMemset once after the allocation): its first 64 bytes
+ * hold the arrival counter of the reductions that pytvb_tv and pytvb_gd_update finish inside the kernel (the last CTA sums the
+ * partials: one launch per call); every call leaves the counter at zero.  One workspace serves one stream at a time. */
 size_t pytvb_reduce_workspace_bytes(const pytvb_problem* pb);
 size_t pytvb_tv_workspace_bytes(const pytvb_problem* pb);
 

@@ -76,8 +76,10 @@ def stream_ptr():
 
 
 def reduce_workspace(pb, device):
+    """Scratch of the calls that produce a scalar.  Zero-initialised: its first 64 bytes are the arrival counter of the reductions
+    that finish inside the producing kernel (pytvb_tv, pytvb_gd_update), which the library leaves at zero after every call."""
     n = _lib.lib().pytvb_reduce_workspace_bytes(ctypes.byref(pb))
-    return torch.empty(n, dtype=torch.uint8, device=device)
+    return torch.zeros(n, dtype=torch.uint8, device=device)
 
 
 def to_output(t, return_pytorch_tensor):

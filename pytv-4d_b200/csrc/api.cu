@@ -40,7 +40,7 @@ size_t pytvb_reduce_workspace_bytes(const pytvb_problem* pb) {
     long long n = max_partials(pb);
     const long long nt = tile_max_blocks(pb);
     if (nt > n) n = nt;
-    return (size_t)(n + REDUCE_STAGE2) * sizeof(double);
+    return (size_t)(n + REDUCE_STAGE2 + REDUCE_HEAD) * sizeof(double);
 }
 
 size_t pytvb_tv_workspace_bytes(const pytvb_problem* pb) {

@@ -92,7 +92,7 @@ int run_dual(const pytvb_problem* pb, const void* xbar, void* y, double lam, dou
     DualArgs<T> a;
     a.Xb = ImgView<T>{(const T*)xbar, (const T*)lo, (const T*)hi, 1};
     a.y = (T*)y;
-    a.partial = d_l21 ? (double*)ws : nullptr;
+    a.partial = d_l21 ? reduce_partials(ws) : nullptr;
     a.P = make_params<T>(pb);
     a.sigma = (T)sigma;
     a.inv_lam = (T)(1.0 / lam);
@@ -113,7 +113,7 @@ int run_primal(const pytvb_problem* pb, int variant, const void* y, void* x, voi
     PrimalArgs<T> a;
     a.Y = FieldView<T>{(const T*)y, (const T*)lo, (const T*)hi};
     a.x = (T*)x; a.aux = (T*)aux; a.x0 = (const T*)x0;
-    a.partial = d_fid ? (double*)ws : nullptr;
+    a.partial = d_fid ? reduce_partials(ws) : nullptr;
     a.P = make_params<T>(pb);
     a.tau = (T)tau; a.c2 = (T)c2;
     a.variant = variant;

@@ -69,7 +69,7 @@ int pytvb_cp_dual_f16y(const pytvb_problem* pb, const void* xbar, void* y_half, 
     DualHArgs a;
     a.Xb = ImgView<float>{(const float*)xbar, (const float*)halo_lo, (const float*)halo_hi, 1};
     a.y = (__half*)y_half;
-    a.partial = d_l21_or_null ? (double*)ws : nullptr;
+    a.partial = d_l21_or_null ? reduce_partials(ws) : nullptr;
     a.P = make_params<float>(pb);
     a.sig = (float)(sigma / lam) * a.P.inv_div;      // (y + sigma D)/lam = y/lam + (sigma/lam) D
     a.lam_proj = 1.0f;                               // projection onto the unit ball
@@ -92,7 +92,7 @@ int pytvb_cp_primal_rof_f16y(const pytvb_problem* pb, const void* y_half, void* 
     PrimalHArgs a;
     a.Y = FieldView<__half>{(const __half*)y_half, (const __half*)halo_lo_half, (const __half*)halo_hi_half};
     a.x = (float*)x; a.xbar = (float*)xbar; a.x0 = (const float*)x0;
-    a.partial = d_fid_or_null ? (double*)ws : nullptr;
+    a.partial = d_fid_or_null ? reduce_partials(ws) : nullptr;
     a.P = make_params<float>(pb);
     a.tau_y = (float)(tau * lam);                    // D^T y = lam D^T (y / lam)
     a.tau = (float)tau;

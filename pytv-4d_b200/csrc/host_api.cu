@@ -14,7 +14,11 @@ size_t voxels(const pytvb_problem* pb) { return (size_t)pb->Nz * pb->M * pb->Ni 
 struct DeviceBuf {
     void* p = nullptr;
     ~DeviceBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t n) { return cudaMalloc(&p, n ? n : 1); }
+    // zeroed: a reduce workspace starts with its arrival counter at 0 (finish_partials)
+    cudaError_t alloc(size_t n) {
+        cudaError_t e = cudaMalloc(&p, n ? n : 1);
+        return e == cudaSuccess ? cudaMemset(p, 0, n ? n : 1) : e;
+    }
 };
 
 // Device copies of the HOST arrays a problem descriptor points to - the (Ni,Nj) byte mask and the (Nz,M,Ni,Nj) time scale;

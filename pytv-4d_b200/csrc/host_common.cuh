@@ -138,6 +138,7 @@ inline int check_grid(const Tiling& tl) {
 
 // Workspace layout for reductions: [partials: max CTAs][stage 2: 256 doubles]
 constexpr int REDUCE_STAGE2 = 256;
+constexpr int REDUCE_HEAD = 8;      // doubles in FRONT of the partials: the arrival counter of finish_partials (at a fixed place, whatever the problem)
 inline long long max_partials(const pytvb_problem* pb) {
     // worst case: scalar path with one row per thread, one extra halo plane on each side (tv sweep 1)
     const Tiling tl = make_tiling((int)pb->Nj, (int)pb->Ni, (int)pb->M, 0, (int)pb->Nz + 2, 1);
@@ -157,6 +158,10 @@ inline int finalize_sum_at(double* partials, long long n, double* stage2, double
     PYTVB_CUDA(cudaGetLastError());
     return PYTVB_OK;
 }
+// Layout of a reduce workspace: [arrival counter of the in-kernel reductions, REDUCE_HEAD doubles][per-CTA partials][second stage].
+// No kernel writes the head except finish_partials, which leaves it zero.
+inline unsigned* reduce_counter(void* ws) { return static_cast<unsigned*>(ws); }
+inline double* reduce_partials(void* ws) { return ws ? static_cast<double*>(ws) + REDUCE_HEAD : nullptr; }
 inline int finalize_sum(double* partials, long long n, double* d_out, cudaStream_t st) {
     return finalize_sum_at(partials, n, partials + n, d_out, st);
 }

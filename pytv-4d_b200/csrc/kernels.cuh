@@ -126,6 +126,40 @@ __device__ __forceinline__ double block_sum(double v) {
     return s;
 }
 
+// Reduction finished inside the producing kernel: every CTA stores its partial; the CTA that arrives last at the counter sums all
+// partials in a fixed order (thread k takes partials k, k + blockDim, ...; then the warps in order) and writes the scalar - no
+// second launch, which is what a launch-bound volume pays for (a 256^2 sub-gradient descent iteration: 19 -> 12 us).  The value
+// does not depend on which CTA is last.  `counter` must be 0 on entry; atomicInc wraps it back to 0 with the last arrival, so a
+// workspace zeroed once stays usable.  block_value: this CTA's partial, valid in thread 0.  counter == nullptr: store the partial only.
+__device__ __forceinline__ void finish_partials(double block_value, double* __restrict__ partial, unsigned* counter, double* __restrict__ d_out) {
+    __shared__ bool is_last;
+    __shared__ double warp_sum[32];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        partial[blockIdx.x] = block_value;
+        bool last = false;
+        if (counter) {
+            __threadfence();
+            last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;
+        }
+        is_last = last;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double v = 0.0;
+    for (unsigned k = tid; k < gridDim.x; k += blockDim.x) v += __ldcg(partial + k);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((tid & 31) == 0) warp_sum[tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) s += warp_sum[w];
+        *d_out = s;
+    }
+}
+
 // Second stage of the reductions: `n` partials -> `nout` partials (contiguous chunks, fixed order).
 static __global__ void __launch_bounds__(CTA_THREADS) reduce_chunks_kernel(const double* __restrict__ in, long long n, double* __restrict__ out, double scale) {
     const long long chunk = (n + gridDim.x - 1) / gridDim.x;
@@ -183,7 +217,7 @@ __global__ void __launch_bounds__(CTA_THREADS) apply_mask_quad_kernel(T* __restr
 // fidelity partial sums sum (x_new - x0)^2, one read of x, x0, G and one write of x.
 template <typename T>
 __global__ void __launch_bounds__(CTA_THREADS) gd_update_kernel(T* __restrict__ x, const T* __restrict__ x0, const T* __restrict__ G, long long V, T step,
-                                                                T lam, double* __restrict__ partial) {
+                                                                T lam, double* __restrict__ partial, unsigned* counter, double* __restrict__ d_out) {
     const long long stride = (long long)gridDim.x * CTA_THREADS;
     T fid = T(0);
     for (long long k = (long long)blockIdx.x * CTA_THREADS + threadIdx.x; k < V; k += stride) {
@@ -195,7 +229,7 @@ __global__ void __launch_bounds__(CTA_THREADS) gd_update_kernel(T* __restrict__ 
     }
     if (partial) {
         const double bs = block_sum((double)fid);
-        if (threadIdx.x == 0) partial[blockIdx.x] = bs;
+        finish_partials(bs, partial, counter, d_out);
     }
 }
 

@@ -23,7 +23,7 @@ namespace pytvb {
 #define PYTVB_TILE_MAXT 512
 #endif
 constexpr int TILE_MAX_THREADS = PYTVB_TILE_MAXT;
-constexpr size_t TILE_SMEM_LIMIT = 227 * 1024 - 256;     // opt-in maximum per CTA on sm_100 minus the static reduction scratch
+constexpr size_t TILE_SMEM_LIMIT = 227 * 1024 - 1024;    // opt-in maximum per CTA on sm_100 minus the static scratch (reductions, mbarriers)
 
 template <typename T>
 inline size_t tile_smem_bytes(const TileGeom& g, bool mask) {
@@ -183,25 +183,25 @@ struct TileStager {
     }
 };
 
-// CTA-wide sum of the threads' TV partials -> partial[blockIdx.x]
-__device__ __forceinline__ void tile_store_partial(double v, double* __restrict__ partial, int nthreads) {
+// CTA-wide sum of the threads' TV partials -> partial[blockIdx.x]; the CTA that finishes last adds the partials up (finish_partials).
+__device__ __forceinline__ void tile_store_partial(double v, double* __restrict__ partial, unsigned* counter, double* __restrict__ d_out, int nthreads) {
     __shared__ double warp_part[TILE_MAX_THREADS / 32];
     const int tid = threadIdx.x;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if ((tid & 31) == 0) warp_part[tid >> 5] = v;
     __syncthreads();
-    if (tid == 0) {
-        double s = 0.0;
+    double s = 0.0;
+    if (tid == 0)
         for (int w = 0; w < (nthreads >> 5); ++w) s += warp_part[w];
-        partial[blockIdx.x] = s;
-    }
+    finish_partials(s, partial, counter, d_out);
 }
 
 // ---- form 1: two phases per plane
 template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, int TSMODE, bool NORMS>
 __global__ void __launch_bounds__(TILE_MAX_THREADS, PYTVB_TILE_MINB)
-tv_tile_kernel(ImgView<T> X, ImgView<T> TS, T* __restrict__ G, T* __restrict__ norms, double* __restrict__ partial, Params<T> P, TileGeom g,
+tv_tile_kernel(ImgView<T> X, ImgView<T> TS, T* __restrict__ G, T* __restrict__ norms, double* __restrict__ partial, unsigned* counter,
+               double* __restrict__ d_tv, Params<T> P, TileGeom g,
                const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapLo, const __grid_constant__ CUtensorMap mapHi) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ __align__(8) unsigned long long stage_bar[4];
@@ -251,13 +251,14 @@ tv_tile_kernel(ImgView<T> X, ImgView<T> TS, T* __restrict__ G, T* __restrict__ n
             __syncthreads();
         }
     }
-    tile_store_partial(st.tv, partial, g.nthreads);
+    tile_store_partial(st.tv, partial, counter, d_tv, g.nthreads);
 }
 
 // ---- form 2: one phase per plane (tile2_core.cuh)
 template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, int TSMODE, bool NORMS>
 __global__ void __launch_bounds__(TILE_MAX_THREADS, PYTVB_TILE_MINB)
-tv_tile2_kernel(ImgView<T> X, ImgView<T> TS, T* __restrict__ G, T* __restrict__ norms, double* __restrict__ partial, Params<T> P, TileGeom g,
+tv_tile2_kernel(ImgView<T> X, ImgView<T> TS, T* __restrict__ G, T* __restrict__ norms, double* __restrict__ partial, unsigned* counter,
+                double* __restrict__ d_tv, Params<T> P, TileGeom g,
                 const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapLo, const __grid_constant__ CUtensorMap mapHi) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ __align__(8) unsigned long long stage_bar[4];
@@ -290,7 +291,7 @@ tv_tile2_kernel(ImgView<T> X, ImgView<T> TS, T* __restrict__ G, T* __restrict__ 
         if (more) sg.land(tile2_slot(p + 2));
         __syncthreads();
     }
-    tile_store_partial(st.tv, partial, g.nthreads);
+    tile_store_partial(st.tv, partial, counter, d_tv, g.nthreads);
 }
 #endif
 

@@ -77,7 +77,7 @@ int run_l21(const pytvb_problem* pb, const void* D, int Nd, void* norms, double*
     Params<T> P = make_params<T>(pb);
     P.sZf = P.sC * Nd;
     const int vec = pick_vec<T>(pb, {D, norms});
-    double* partial = (double*)ws;
+    double* partial = reduce_partials(ws);
     {
         constexpr int R = PYTVB_STRIP_R;
         const Tiling tl = make_strip_tiling<R>(P.Nj, P.Ni, P.M, P.Nz, vec);
@@ -140,14 +140,16 @@ int pytvb_gd_update(const pytvb_problem* pb, void* x, const void* x0, const void
     const long long V = (long long)pb->Ni * pb->Nj * pb->M * pb->Nz;
     long long nb = (V + CTA_THREADS - 1) / CTA_THREADS;
     if (nb > 148 * 8) nb = 148 * 8;
-    double* partial = d_fid_or_null ? (double*)ws : nullptr;
+    double* partial = d_fid_or_null ? reduce_partials(ws) : nullptr;
+    unsigned* counter = d_fid_or_null ? reduce_counter(ws) : nullptr;       // the sum is finished by the last CTA: one launch
     if (pb->dtype == PYTVB_F32)
-        gd_update_kernel<float><<<(unsigned)nb, CTA_THREADS, 0, st>>>((float*)x, (const float*)x0, (const float*)G, V, (float)step, (float)lam, partial);
+        gd_update_kernel<float><<<(unsigned)nb, CTA_THREADS, 0, st>>>((float*)x, (const float*)x0, (const float*)G, V, (float)step, (float)lam, partial, counter,
+                                                                      d_fid_or_null);
     else
-        gd_update_kernel<double><<<(unsigned)nb, CTA_THREADS, 0, st>>>((double*)x, (const double*)x0, (const double*)G, V, step, lam, partial);
+        gd_update_kernel<double><<<(unsigned)nb, CTA_THREADS, 0, st>>>((double*)x, (const double*)x0, (const double*)G, V, step, lam, partial, counter, d_fid_or_null);
     count_launches(1);
     PYTVB_CUDA(cudaGetLastError());
-    return d_fid_or_null ? finalize_sum(partial, nb, d_fid_or_null, st) : PYTVB_OK;
+    return PYTVB_OK;
 }
 
 int pytvb_apply_mask(const pytvb_problem* pb, void* x, const uint8_t* mask, int mask_is_plane, void* stream) {

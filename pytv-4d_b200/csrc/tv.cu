@@ -58,7 +58,7 @@ int run_tv(const pytvb_problem* pb, const void* x, void* G, void* norms, double*
     a.W = ImgView<T>{a.Wz0, wbuf, a.Wz0 + (long long)a.P.Nz * a.P.sZ, 1};
     a.G = (T*)G;
     a.norms = (T*)norms;
-    a.partial = (double*)ws_reduce;
+    a.partial = reduce_partials(ws_reduce);
     a.z_lo = has_lo ? -1 : 0;
     a.nz = (int)pb->Nz + (has_lo ? 1 : 0) + (has_hi ? 1 : 0);
     a.st = st;
@@ -67,7 +67,9 @@ int run_tv(const pytvb_problem* pb, const void* x, void* G, void* norms, double*
     a.TS = ImgView<T>{a.P.tscale, (const T*)pb->time_scale_lo, (const T*)pb->time_scale_hi, 1};
     const int vec = pick_vec<T>(pb, {x, G, norms, lo2, hi2, pb->time_scale_lo, pb->time_scale_hi});
     if (tv_uses_tile(pb)) {
-        if (int rc = run_tv_tile<T>(vec, pb->scheme, ax.z_on, ax.t_on, a)) return rc;
+        a.counter = reduce_counter(ws_reduce);
+        a.d_out = d_tv;
+        return run_tv_tile<T>(vec, pb->scheme, ax.z_on, ax.t_on, a);       // one launch: the last CTA writes d_tv
     } else {
         PYTVB_REQUIRE(!(pb->time_scale && (lo2 || hi2)), "time_scale on slabs with z halos needs the single-sweep kernel (not this problem: > 16 coupled frames or a centred length-2 axis)");
         if (int rc = dispatch<LaunchTv, T>(vec, pb->scheme, ax.z_on, ax.t_on, a)) return rc;
@@ -101,7 +103,7 @@ int run_tv_value(const pytvb_problem* pb, const void* x, double* d_tv, const voi
     const Axes ax = axes_of(pb);
     TvValArgs<T> a;
     a.X = ImgView<T>{(const T*)x, (const T*)lo, (const T*)hi, 1};
-    a.partial = (double*)ws;
+    a.partial = reduce_partials(ws);
     a.P = make_params<T>(pb);
     a.st = st;
     long long nb = 0;

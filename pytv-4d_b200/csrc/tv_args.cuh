@@ -8,6 +8,7 @@ template <typename T> struct TvArgs {
     ImgView<T> X; ImgView<T> W; T* Wz0; T* G; T* norms; double* partial; Params<T> P; int z_lo, nz; cudaStream_t st;
     long long* nblocks_out;
     ImgView<T> TS;      // time-scale map with its one-plane z halos (tile kernel)
+    unsigned* counter; double* d_out;      // tile kernel: arrival counter and destination of the TV value (the last CTA finishes the sum)
 };
 
 // tv_tile.cu

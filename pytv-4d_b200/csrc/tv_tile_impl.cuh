@@ -34,7 +34,7 @@ int launch_tile(const TvArgs<T>& a, const TileGeom& g, size_t smem) {
     if (rc1 != PYTVB_OK) return rc1;
     const int rc2 = make_image_tmap<T>(&mhi, tma ? a.X.hi : nullptr, a.X.depth, a.P.M, a.P.Ni, a.P.Nj, g.FC, g.rowsX, g.pitchX);
     if (rc2 != PYTVB_OK) return rc2;
-    kern<<<(unsigned)g.nblocks, g.nthreads, smem, a.st>>>(a.X, a.TS, a.G, a.norms, a.partial, a.P, g, mx, mlo, mhi);
+    kern<<<(unsigned)g.nblocks, g.nthreads, smem, a.st>>>(a.X, a.TS, a.G, a.norms, a.partial, a.counter, a.d_out, a.P, g, mx, mlo, mhi);
     count_launches(1);
     PYTVB_CUDA(cudaGetLastError());
     *a.nblocks_out = g.nblocks;
