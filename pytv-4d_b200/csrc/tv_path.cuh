@@ -40,8 +40,8 @@ inline bool tv_tile_possible(const pytvb_problem* pb) {
 }
 
 // Which implementation runs.  Both are parity-green on every golden; the choice is measured speed (DESIGN.md 3.3,
-// profiles/r02n_tv_times.txt; C4 slab, ms, tile / sweeps: hybrid 1.96 / 2.68, upwind 1.68 / 2.29, centred 2.23 / 3.67; C5 slab hybrid
-// 7.6 / 11.4; 512^3 hybrid 0.64 / 0.64, upwind 0.56 / 0.62): the tile kernel wherever it can take the problem.  It moves 1.07 x the
+// profiles/r02z_tv_times.txt; C4 slab, ms, tile / sweeps: hybrid 1.83 / 2.71, upwind 1.59 / 2.31, centred 1.91 / 3.54; C5 slab hybrid
+// 7.5 / 11.4; 512^3 hybrid 0.49 / 0.64, upwind 0.44 / 0.62): the tile kernel wherever it can take the problem.  It moves 1.03 x the
 // algorithmic 8 B/voxel (the sweeps 2.5 x), needs no workspace and is one launch.
 inline bool tv_uses_tile(const pytvb_problem* pb) {
     const TvPathMode m = tv_path_mode();
