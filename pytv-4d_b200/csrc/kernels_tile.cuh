@@ -31,7 +31,8 @@ inline size_t tile_smem_bytes(const TileGeom& g, bool mask) {
     size_t b = 128 + ((size_t)2 * g.padf + (size_t)g.nslots * g.xslot + (size_t)g.nwbuf * g.wbuf) * sizeof(T);
     b = (b + 15) & ~size_t(15);
     b += (size_t)g.FC * g.rowsX * (sizeof(long long) + sizeof(int));       // staging tables
-    if (mask) b += (size_t)g.RPF * g.WJ;
+    b = (b + 15) & ~size_t(15);
+    if (mask) b += (size_t)g.RPF * g.WJ * sizeof(T);                        // static-mask factors of the work region
     return (b + 15) & ~size_t(15);
 }
 
@@ -132,7 +133,8 @@ PYTVB_HD TileCtx<T> tile_ctx(const TileGeom& g, long long b, const Params<T>& P,
     size_t off = (((size_t)2 * g.padf + (size_t)g.nslots * g.xslot + (size_t)g.nwbuf * g.wbuf) * sizeof(T) + 15) & ~size_t(15);
     c.rowg = reinterpret_cast<long long*>(smem + off);
     c.rowd = reinterpret_cast<int*>(c.rowg + (size_t)g.FC * g.rowsX);
-    c.Ms = mask ? reinterpret_cast<uint8_t*>(c.rowd + (size_t)g.FC * g.rowsX) : nullptr;
+    off = (off + (size_t)g.FC * g.rowsX * (sizeof(long long) + sizeof(int)) + 15) & ~size_t(15);
+    c.Ms = mask ? reinterpret_cast<T*>(smem + off) : nullptr;
     return c;
 }
 

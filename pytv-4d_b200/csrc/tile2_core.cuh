@@ -215,9 +215,9 @@ PYTVB_HD void tile2_step_ph(Tile2Thread<T, VEC, R>& st, const TileCtx<T>& c, con
             }
             if constexpr (TSMODE >= 1) {
                 if (c.Ms) {
-                    const uint8_t* m = c.Ms + (rr + 1) * WJ + tp.cj + VEC;
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) v[e] *= m[e] ? P.sfac : T(1);
+                    T f[VEC];
+                    ld_into<T, VEC>(f, c.Ms + (rr + 1) * WJ + tp.cj + VEC);
+                    V::mul(v, v, f);
                 }
             }
             V::add(gq, gq, v);

@@ -125,7 +125,9 @@ template <typename T>
 struct TileCtx {
     T* Xs;             // [3][FC][slotX]
     T* Ws;             // [FC][slotW]
-    uint8_t* Ms;       // [RPF][WJ] static-mask bytes of the work region, or null
+    T* Ms;             // [RPF][WJ] factor of the time component(s) from the static mask over the work region (sqrt(factor_reg_static) on
+                       // static pixels, 1 elsewhere), or null.  As values, not mask bytes: one 128-bit load per row and part instead of a
+                       // 32-bit load and four selects (mask_static cost 19-21 % of the kernel on the C5 slab, profiles/r02z_launches_c5.csv)
     long long* rowg;   // [FC * rowsX] staging table: element offset of window row r inside a z-plane group (frame and clamped row)
     int* rowd;         // [FC * rowsX] staging table: element offset of window row r inside a slot group (frame, row)
     int i0, j0, t0;    // global row / column of tile (0, 0); first frame
@@ -306,13 +308,13 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const void* map, unsigned
 }
 #endif
 
-// Static-mask bytes of the work region (clamped), once per CTA.
+// Static-mask factors of the work region (clamped), once per CTA.
 template <typename T, int VEC>
 PYTVB_HD void tile_stage_mask(const TileCtx<T>& c, const TileGeom& g, const Params<T>& P, int tid) {
     for (int k = tid; k < g.RPF * g.WJ; k += g.nthreads) {
         const int r = k / g.WJ, cc = k - r * g.WJ;
         const int gi = clampi(c.i0 + r - 1, 0, P.Ni - 1), gj = clampi(c.j0 + cc - VEC, 0, P.Nj - 1);
-        c.Ms[k] = P.mask_static[(long long)gi * P.Nj + gj];
+        c.Ms[k] = P.mask_static[(long long)gi * P.Nj + gj] ? P.sfac : T(1);
     }
 }
 
@@ -363,11 +365,7 @@ PYTVB_HD void tile_time_factor(T* f, const TileCtx<T>& c, const TileGeom& g, con
 #pragma unroll
     for (int e = 0; e < VEC; ++e) f[e] = T(1);
     if constexpr (TSMODE >= 1) {
-        if (c.Ms) {
-            const uint8_t* m = c.Ms + wr * TileC<VEC>::WJ + cj + VEC;
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) f[e] = m[e] ? P.sfac : T(1);
-        }
+        if (c.Ms) ld_into<T, VEC>(f, c.Ms + wr * TileC<VEC>::WJ + cj + VEC);
     }
     if constexpr (TSMODE == 2) {
         const int gi = clampi(c.i0 + wr - 1, 0, P.Ni - 1);
@@ -818,9 +816,9 @@ PYTVB_HD void tile_phase_g(TileThread<T, VEC, R>& st, const TileCtx<T>& c, const
             }
             if constexpr (TSMODE >= 1) {
                 if (c.Ms) {
-                    const uint8_t* m = c.Ms + (rr + 1) * WJ + wcol;
-#pragma unroll
-                    for (int e = 0; e < VEC; ++e) v[e] *= m[e] ? P.sfac : T(1);
+                    T f[VEC];
+                    ld_into<T, VEC>(f, c.Ms + (rr + 1) * WJ + wcol);
+                    V::mul(v, v, f);
                 }
             }
             V::add(gq, gq, v);
