@@ -70,6 +70,8 @@ struct Params {
     const T* tscale;              // (Nz, M, Ni, Nj) per-voxel factor of the time component(s) (sqrt of a weight map); or null
     long long sT, sZ;             // image strides (elements): Ni*Nj, M*Ni*Nj
     long long sC, sZf;            // field strides: component = M*Ni*Nj, plane group = Nd*M*Ni*Nj
+    unsigned* red_counter;        // strip kernels with a scalar output: arrival counter and destination of the sum when a small grid
+    double* red_out;              // finishes its reduction inside the kernel (kernels.cuh::store_or_finish); null otherwise
 };
 
 // Image with optional z-halo planes (multi-GPU slabs).  `lo` holds `depth` planes z = -depth .. -1 in

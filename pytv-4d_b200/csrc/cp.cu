@@ -94,6 +94,7 @@ int run_dual(const pytvb_problem* pb, const void* xbar, void* y, double lam, dou
     a.y = (T*)y;
     a.partial = d_l21 ? reduce_partials(ws) : nullptr;
     a.P = make_params<T>(pb);
+    arm_reduction(a.P, ws, d_l21);
     a.sigma = (T)sigma;
     a.inv_lam = (T)(1.0 / lam);
     a.lam = (T)lam;
@@ -103,7 +104,7 @@ int run_dual(const pytvb_problem* pb, const void* xbar, void* y, double lam, dou
     a.nb = &nb;
     const int vec = pick_vec<T>(pb, {xbar, y, lo, hi, mir_prev, mir_next});
     if (int rc = dispatch<LaunchDual, T>(vec, pb->scheme, ax.z_on, ax.t_on, a)) return rc;
-    return d_l21 ? finalize_sum(a.partial, nb, d_l21, st) : PYTVB_OK;
+    return d_l21 ? finish_reduction(a.partial, nb, d_l21, st) : PYTVB_OK;
 }
 
 template <typename T>
@@ -115,6 +116,7 @@ int run_primal(const pytvb_problem* pb, int variant, const void* y, void* x, voi
     a.x = (T*)x; a.aux = (T*)aux; a.x0 = (const T*)x0;
     a.partial = d_fid ? reduce_partials(ws) : nullptr;
     a.P = make_params<T>(pb);
+    arm_reduction(a.P, ws, d_fid);
     a.tau = (T)tau; a.c2 = (T)c2;
     a.variant = variant;
     a.mir_prev = (T*)mir_prev; a.mir_next = (T*)mir_next;
@@ -123,7 +125,7 @@ int run_primal(const pytvb_problem* pb, int variant, const void* y, void* x, voi
     a.nb = &nb;
     const int vec = pick_vec<T>(pb, {y, x, aux, x0, lo, hi, mir_prev, mir_next});
     if (int rc = dispatch<LaunchPrimal, T>(vec, pb->scheme, ax.z_on, ax.t_on, a)) return rc;
-    return d_fid ? finalize_sum(a.partial, nb, d_fid, st) : PYTVB_OK;
+    return d_fid ? finish_reduction(a.partial, nb, d_fid, st) : PYTVB_OK;
 }
 
 }  // namespace

@@ -82,6 +82,8 @@ inline Params<T> make_params(const pytvb_problem* pb) {
     P.sZ = P.sT * pb->M;
     P.sC = P.sZ;
     P.sZf = P.sC * a.Nd;
+    P.red_counter = nullptr;
+    P.red_out = nullptr;
     return P;
 }
 
@@ -162,6 +164,17 @@ inline int finalize_sum_at(double* partials, long long n, double* stage2, double
 // No kernel writes the head except finish_partials, which leaves it zero.
 inline unsigned* reduce_counter(void* ws) { return static_cast<unsigned*>(ws); }
 inline double* reduce_partials(void* ws) { return ws ? static_cast<double*>(ws) + REDUCE_HEAD : nullptr; }
+// Strip kernels: grids of up to REDUCE_IN_KERNEL_MAX CTAs finish their sum inside the kernel (the launch-bound sizes: a second launch
+// costs as much as the kernel), larger ones through the two-stage reduction.  arm_reduction before the launch, finish_reduction after.
+template <typename T>
+inline void arm_reduction(Params<T>& P, void* ws, double* d_out) {
+    P.red_counter = d_out ? reduce_counter(ws) : nullptr;
+    P.red_out = d_out;
+}
+inline int finalize_sum(double* partials, long long n, double* d_out, cudaStream_t st);
+inline int finish_reduction(double* partials, long long n, double* d_out, cudaStream_t st) {
+    return n <= REDUCE_IN_KERNEL_MAX ? PYTVB_OK : finalize_sum(partials, n, d_out, st);
+}
 inline int finalize_sum(double* partials, long long n, double* d_out, cudaStream_t st) {
     return finalize_sum_at(partials, n, partials + n, d_out, st);
 }

@@ -160,6 +160,15 @@ __device__ __forceinline__ void finish_partials(double block_value, double* __re
     }
 }
 
+// Strip kernels: a small grid finishes its sum in the kernel, a large one leaves the partials to the two-stage reduction
+// (host_common.cuh::finish_reduction applies the same rule).  Called by all threads of the CTA; block_value valid in thread 0.
+constexpr unsigned REDUCE_IN_KERNEL_MAX = 8192;
+template <typename PT>
+__device__ __forceinline__ void store_or_finish(double block_value, double* __restrict__ partial, const PT& P) {
+    if (P.red_out && gridDim.x <= REDUCE_IN_KERNEL_MAX) finish_partials(block_value, partial, P.red_counter, P.red_out);
+    else if (threadIdx.x == 0) partial[blockIdx.x] = block_value;
+}
+
 // Second stage of the reductions: `n` partials -> `nout` partials (contiguous chunks, fixed order).
 static __global__ void __launch_bounds__(CTA_THREADS) reduce_chunks_kernel(const double* __restrict__ in, long long n, double* __restrict__ out, double scale) {
     const long long chunk = (n + gridDim.x - 1) / gridDim.x;

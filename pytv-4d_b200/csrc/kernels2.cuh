@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(CTA_THREADS, PYTVB_DUAL_MINB) cp_dual_strip_ke
     }
     if (partial) {
         const double bs = block_sum((double)l21 * (double)P.inv_div);
-        if (threadIdx.x == 0) partial[blockIdx.x] = bs;
+        store_or_finish(bs, partial, P);
     }
 }
 
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(CTA_THREADS, PYTVB_PRIMAL_MINB) cp_primal_stri
     }
     if (partial) {
         const double bs = block_sum((double)fid);
-        if (threadIdx.x == 0) partial[blockIdx.x] = bs;
+        store_or_finish(bs, partial, P);
     }
 }
 
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(CTA_THREADS) l21_strip_kernel(const T* __restr
         });
     }
     const double bs = block_sum((double)sum);
-    if (threadIdx.x == 0) partial[blockIdx.x] = bs;
+    store_or_finish(bs, partial, P);
 }
 
 // TV sweep 1 (strip form): z range tl.z_lo .. tl.z_lo+tl.nz-1 includes one halo plane per side when present.
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(CTA_THREADS, PYTVB_TVNORM_MINB) tv_norm_strip_
         }
     }
     const double bs = block_sum((double)sum);
-    if (threadIdx.x == 0) partial[blockIdx.x] = bs;
+    store_or_finish(bs, partial, P);
 }
 
 template <typename T, int VEC, int SCHEME, bool Z_ON, bool T_ON, int R, bool TS = false, bool FAC = true>

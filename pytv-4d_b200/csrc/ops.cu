@@ -76,6 +76,7 @@ template <typename T>
 int run_l21(const pytvb_problem* pb, const void* D, int Nd, void* norms, double* d_sum, void* ws, cudaStream_t st) {
     Params<T> P = make_params<T>(pb);
     P.sZf = P.sC * Nd;
+    arm_reduction(P, ws, d_sum);
     const int vec = pick_vec<T>(pb, {D, norms});
     double* partial = reduce_partials(ws);
     {
@@ -98,7 +99,7 @@ int run_l21(const pytvb_problem* pb, const void* D, int Nd, void* norms, double*
 #undef PYTVB_L21
         count_launches(1);
         PYTVB_CUDA(cudaGetLastError());
-        return finalize_sum(partial, tl.nblocks, d_sum, st);
+        return finish_reduction(partial, tl.nblocks, d_sum, st);
     }
 }
 

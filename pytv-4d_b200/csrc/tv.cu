@@ -105,12 +105,13 @@ int run_tv_value(const pytvb_problem* pb, const void* x, double* d_tv, const voi
     a.X = ImgView<T>{(const T*)x, (const T*)lo, (const T*)hi, 1};
     a.partial = reduce_partials(ws);
     a.P = make_params<T>(pb);
+    arm_reduction(a.P, ws, d_tv);
     a.st = st;
     long long nb = 0;
     a.nb = &nb;
     const int vec = pick_vec<T>(pb, {x, lo, hi});
     if (int rc = dispatch<LaunchTvVal, T>(vec, pb->scheme, ax.z_on, ax.t_on, a)) return rc;
-    return finalize_sum(a.partial, nb, d_tv, st);
+    return finish_reduction(a.partial, nb, d_tv, st);
 }
 }  // namespace
 
