@@ -29,6 +29,18 @@ def test_header_symbols_are_exported_and_bound():
     assert _lib.lib().pytvb_version() == 101
 
 
+def test_build_id_names_the_sources():
+    """pytvb_build_id() = hash of the sources the library was built from (what profiles/traffic.json is keyed by): 16 hex digits, and
+    equal to the hash of the sources in this tree when the library is fresh (build() asserts the same)."""
+    import re
+    import sys
+    bid = _lib.lib().pytvb_build_id().decode()
+    assert re.fullmatch(r"[0-9a-f]{16}", bid), bid
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import __graft_entry__ as g
+    assert bid == g.source_hash()
+
+
 def test_problem_struct_layout_matches_header():
     # 2 x int32, 6 x int64, 3 x double, 4 pointers, no padding surprises
     assert ctypes.sizeof(_lib.Problem) == 8 + 6 * 8 + 3 * 8 + 4 * 8
