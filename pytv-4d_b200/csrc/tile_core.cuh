@@ -8,16 +8,19 @@
 // C(m) = (x_{m+1} - x_{m-1}) * w_m and G(v) = C(v-e) - C(v+e).  So G(v) needs w at distance 1 and x at distance 2.
 //
 // One launch, x read once, G written once (8 B/voxel): a CTA owns an in-plane tile (TI x TJ output voxels, all M time
-// frames when the time axis is on) and marches along z.  Per z-plane p ("step"):
-//   * x(p+2) arrives in shared memory (cp.async issued one step ahead; the window holds the tile plus 2 halo rows / columns
-//     with indices CLAMPED at the volume boundary, so every out-of-range difference is exactly 0 - the reference's rule,
-//     tv_operators_CPU.py:118 - without predicates; zero fill would be wrong);
+// frames when the time axis is on) and marches along z.  This file holds what both forms of the kernel share - geometry, the
+// staging of the x windows (TMA on the vector path, per-thread cp.async on the scalar path), the thread coordinates, the norm -
+// and the per-thread code of FORM 1, two phases per z-plane p ("step"):
+//   * x(p+2) arrives in shared memory one step ahead.  The window holds the tile plus 2 halo rows / columns; at the volume
+//     boundary the cell just outside takes the boundary value, so every out-of-range difference is exactly 0 - the reference's
+//     rule, tv_operators_CPU.py:118 - without predicates (TMA's zero fill alone would be wrong: tile_fixup_plane);
 //   * w-phase: every thread computes n(p), w(p) for its R rows x one quad column (tile + 1 halo ring), publishes w(p) to
-//     shared memory, forms the z edge term between planes p-1 and p from registers and with it completes and stores G(p-1);
-//   * barrier; G-phase: the in-plane and time edge terms of plane p from the x / w tiles -> kept in registers until the
-//     next step supplies the z term.
-// z neighbours live in registers (each thread keeps, per owned voxel: the raw z difference, w and the running G: 3 values),
-// in-plane and time neighbours in shared memory (3 x-planes x M frames, 1 w-plane x M frames).
+//     shared memory, forms the z edge term between planes p-1 and p and with it completes and stores G(p-1);
+//   * barrier; G-phase: the in-plane and time edge terms of plane p from the x / w windows -> kept in registers until the
+//     next step supplies the z term; barrier.
+// z neighbours live in registers (per owned voxel: the raw z difference, the running G and - within a step - w and the z term),
+// in-plane and time neighbours in shared memory (3 x-planes x M frames, 1 w-plane x M frames).  FORM 2 (tile2_core.cuh) runs one
+// phase and one barrier per plane with a 4-slot x ring and two w windows; kernels_tile.cuh picks the form and holds the kernels.
 // Everything here is __host__ __device__ and index-pure: tests/emul runs the same code thread by thread on the CPU.
 #pragma once
 #include "strip_core.cuh"
@@ -123,8 +126,8 @@ struct TileC {
 
 template <typename T>
 struct TileCtx {
-    T* Xs;             // [3][FC][slotX]
-    T* Ws;             // [FC][slotW]
+    T* Xs;             // [nslots] x windows, xslot elements apart, each [FC][slotX]
+    T* Ws;             // [nwbuf] w windows, wbuf elements apart, each [FC][slotW]
     T* Ms;             // [RPF][WJ] factor of the time component(s) from the static mask over the work region (sqrt(factor_reg_static) on
                        // static pixels, 1 elsewhere), or null.  As values, not mask bytes: one 128-bit load per row and part instead of a
                        // 32-bit load and four selects (mask_static cost 19-21 % of the kernel on the C5 slab, profiles/r02z_launches_c5.csv)
@@ -245,21 +248,24 @@ PYTVB_HD void tile_fixup_plane(const TileCtx<T>& c, const TileGeom& g, const Par
     const int iw = c.i0 - 2, jw = c.j0 - 2 * VEC;           // image row / column of window cell (0, 0)
     const int rT = -iw, rB = P.Ni - 1 - iw, cL = -jw, cR = P.Nj - 1 - jw;      // window row / column of the image's first / last
     const int nq = g.pitchX / VEC;
-    // rows: the row just above the image <- row 0, the row just below <- the last row (in-image columns)
-    for (int k = tid; k < g.FC * 2 * nq; k += g.nthreads) {
-        const int q = k % nq, rest = k / nq, side = rest & 1, fl = rest >> 1;
-        const int rs = side ? rB : rT, rd = side ? rB + 1 : rT - 1;
-        if (rd < 0 || rd >= g.rowsX || q * VEC < cL || q * VEC + VEC - 1 > cR) continue;
-        T* base = slot + (long long)fl * g.slotX + q * VEC;
-        st_pack<T, VEC>(base + rd * g.pitchX, ld_pack<T, VEC>(base + rs * g.pitchX));
-    }
-    // columns: the cell left of the image <- column 0, the cell right of it <- the last column (in-image rows)
-    for (int k = tid; k < g.FC * g.rowsX * 2; k += g.nthreads) {
-        const int side = k & 1, rq = k >> 1, fl = rq / g.rowsX, xr = rq - fl * g.rowsX;
-        const int cs = side ? cR : cL, cd = side ? cR + 1 : cL - 1;
-        if (cd < 0 || cd >= g.pitchX || xr < rT || xr > rB) continue;
-        T* row = slot + (long long)fl * g.slotX + xr * g.pitchX;
-        row[cd] = row[cs];
+    // rows: the row just above the image <- row 0, the row just below <- the last row (in-image columns).  (Loops over the frames
+    // with the thread index as the item: no integer divisions in a piece of code the border CTAs run every step.)
+    for (int fl = 0; fl < g.FC; ++fl) {
+        T* frame = slot + (long long)fl * g.slotX;
+        for (int idx = tid; idx < 2 * nq; idx += g.nthreads) {
+            const int side = idx >= nq ? 1 : 0, q = idx - side * nq;
+            const int rs = side ? rB : rT, rd = side ? rB + 1 : rT - 1;
+            if (rd < 0 || rd >= g.rowsX || q * VEC < cL || q * VEC + VEC - 1 > cR) continue;
+            st_pack<T, VEC>(frame + rd * g.pitchX + q * VEC, ld_pack<T, VEC>(frame + rs * g.pitchX + q * VEC));
+        }
+        // columns: the cell left of the image <- column 0, the cell right of it <- the last column (in-image rows)
+        for (int idx = tid; idx < 2 * g.rowsX; idx += g.nthreads) {
+            const int side = idx & 1, xr = idx >> 1;
+            const int cs = side ? cR : cL, cd = side ? cR + 1 : cL - 1;
+            if (cd < 0 || cd >= g.pitchX || xr < rT || xr > rB) continue;
+            T* row = frame + xr * g.pitchX;
+            row[cd] = row[cs];
+        }
     }
 }
 
