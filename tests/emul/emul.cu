@@ -545,4 +545,24 @@ extern "C" int pytvb_emulate_f16y(int op, const pytvb_problem* pb, const void* i
 
 extern "C" void pytvb_emulate_set_rows(int r) { g_emul_rows = (r == 4) ? 4 : 8; }
 extern "C" void pytvb_emulate_set_tile(int strips, int Lz, int form) { g_tile_strips = strips; g_tile_Lz = Lz; g_tile_form = form; }
+// Geometry the library picks for a float32 (VEC 4) / float64 (VEC 2) problem: out = {form, strips, RPF, TI, TJ, FC, nthreads, Lz, nzc,
+// nblocks, shared-memory bytes, shared-memory limit}.  Host code only (kernels_tile.cuh::pick_tile_form).
+extern "C" int pytvb_emulate_tile_geom(const pytvb_problem* pb, long long* out) {
+    const Axes ax = axes_of(pb);
+    const bool mask = ax.t_on && pb->mask_static;
+    TileGeom g;
+    int form;
+    size_t smem;
+    if (pb->dtype == PYTVB_F32) {
+        form = pick_tile_form<float, 4, PYTVB_TILE_R>(g, (int)pb->Nz, (int)pb->M, (int)pb->Ni, (int)pb->Nj, ax.t_on, mask);
+        smem = form ? tile_smem_bytes<float>(g, mask) : 0;
+    } else {
+        form = pick_tile_form<double, 2, PYTVB_TILE_R>(g, (int)pb->Nz, (int)pb->M, (int)pb->Ni, (int)pb->Nj, ax.t_on, mask);
+        smem = form ? tile_smem_bytes<double>(g, mask) : 0;
+    }
+    if (!form) { out[0] = 0; return 0; }
+    const long long v[12] = {form, g.strips, g.RPF, g.TI, g.TJ, g.FC, g.nthreads, g.Lz, g.nzc, g.nblocks, (long long)smem, (long long)TILE_SMEM_LIMIT};
+    for (int k = 0; k < 12; ++k) out[k] = v[k];
+    return 0;
+}
 extern "C" const char* pytvb_emulate_error(void) { return g_err; }

@@ -52,6 +52,16 @@ def set_tile(strips=0, Lz=0, form=0):
     emul().pytvb_emulate_set_tile(int(strips), int(Lz), int(form))
 
 
+def tile_geometry(shape, dtype=np.float32, scheme="hybrid", reg_z_over_reg=1.0, reg_time=0.0, mask_static=None, fac=0.0):
+    """The tile-kernel form and geometry the library picks for a whole volume of this shape (host logic of kernels_tile.cuh)."""
+    x = np.zeros((1, 1, 1, 4), dtype=dtype)       # only the dtype matters
+    pb, keep = _problem(scheme, x.dtype, shape, reg_z_over_reg, reg_time, mask_static, fac)
+    out = (ctypes.c_longlong * 12)()
+    emul().pytvb_emulate_tile_geom(ctypes.byref(pb), out)
+    keys = ("form", "strips", "RPF", "TI", "TJ", "FC", "nthreads", "Lz", "nzc", "nblocks", "smem", "smem_limit")
+    return dict(zip(keys, [int(v) for v in out]))
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 

@@ -403,3 +403,27 @@ def test_time_weight_map(scheme, shape, scalar):
         assert 0.5 * fid + 0.1 * l21 == pytest.approx(e_ref, rel=1e-12)
     finally:
         em.GEN = old
+
+
+# ------------------------------------------------------------------ tile-kernel geometry (host logic of kernels_tile.cuh)
+def test_tile_kernel_form_and_geometry_for_the_baseline_configs():
+    """Which form of the single-sweep kernel the library picks, and with which tile, for the BASELINE configurations: the one-phase
+    form (4 x slots + 2 w windows) for up to four coupled frames, the two-phase form where the fourth slot would cost tile rows;
+    the shared-memory footprint stays inside the opt-in limit; z chunks fill the 148 SMs in whole waves."""
+    g = em.tile_geometry((128, 4, 1024, 1024), np.float32, reg_time=2 ** -5)                  # C4 slab
+    assert (g["form"], g["FC"], g["strips"], g["TI"], g["TJ"], g["nthreads"]) == (2, 4, 4, 14, 120, 512)
+    assert g["smem"] <= g["smem_limit"] <= 227 * 1024 and g["smem"] > 200 * 1024
+    assert g["nblocks"] == 74 * 9 * g["nzc"] and g["nblocks"] % 148 == 0 and g["Lz"] * g["nzc"] >= 128
+    g = em.tile_geometry((64, 8, 2048, 2048), np.float32, reg_time=2 ** -5)                   # C5 slab: eight coupled frames
+    assert (g["form"], g["FC"], g["strips"], g["TI"]) == (1, 8, 2, 6)
+    assert g["smem"] <= g["smem_limit"]
+    g = em.tile_geometry((64, 8, 2048, 2048), np.float32, reg_time=2 ** -5, mask_static=np.ones((2048, 2048), bool), fac=4.0)
+    assert (g["form"], g["strips"]) == (1, 2) and g["smem"] <= g["smem_limit"]                 # the mask-factor tile still fits
+    g = em.tile_geometry((512, 1, 512, 512), np.float32)                                      # C3: no time axis, 16 strips of one frame
+    assert (g["form"], g["FC"], g["strips"], g["TI"]) == (2, 1, 16, 62) and g["smem"] <= g["smem_limit"]
+    g = em.tile_geometry((20, 4, 100, 100), np.float64, reg_time=2 ** -5)                     # C2 (README volume, float64)
+    assert g["form"] == 2 and g["TJ"] == 60 and g["Lz"] <= 4 and g["nblocks"] <= 148          # short z chunks: one wave of CTAs
+    g = em.tile_geometry((1, 1, 256, 256), np.float32)                                        # C1: one plane
+    assert g["form"] in (1, 2) and g["nzc"] == 1 and g["smem"] <= g["smem_limit"]
+    g = em.tile_geometry((4, 32, 64, 64), np.float32, reg_time=1.0)                           # more coupled frames than the CTA has warps
+    assert g["form"] == 0                                                                     # -> two-sweep fallback
