@@ -173,6 +173,16 @@ struct TileStager {
             tile_stage_plane<T, VEC>(c, g, X, P, ql, s, tid);
         }
     }
+    // L2 prefetch of plane ql (vector path; the scalar path has no tensor map)
+    __device__ __forceinline__ void prefetch(int ql) {
+        if constexpr (TMA) {
+            if (tid == 0) {
+                const CUtensorMap* m = ql < 0 ? mapLo : (ql >= P.Nz ? mapHi : mapX);
+                const int zi = ql < 0 ? ql + X.depth : (ql >= P.Nz ? ql - P.Nz : ql);
+                tma_prefetch_4d(m, c.j0 - 2 * VEC, c.i0 - 2, c.t0, zi);
+            }
+        }
+    }
     // the plane of slot s has landed (and is repaired); a __syncthreads must follow before other threads' cells are read
     __device__ __forceinline__ void land(int s) {
         if constexpr (TMA) {
@@ -229,6 +239,7 @@ tv_tile_kernel(ImgView<T> X, ImgView<T> TS, T* __restrict__ G, T* __restrict__ n
         for (int p = p0; p <= p1; ++p) {
             const bool more = p + 2 <= p1 + 1;
             if (more) sg.issue(tile_clamp_plane(P, p + 2), tile_slot(p + 2));
+            if (p + 3 <= p1 + 1) sg.prefetch(tile_clamp_plane(P, p + 3));
             tile_phase_w<T, VEC, SCHEME, Z_ON, T_ON, R, TSMODE, NORMS>(st, c, g, P, TS, G, norms, p, tp);
             __syncthreads();
             if (p >= c.zc0 && p < c.zc1) tile_phase_g<T, VEC, SCHEME, Z_ON, T_ON, R, TSMODE>(st, c, g, P, TS, G, p, tp);
@@ -284,11 +295,13 @@ tv_tile2_kernel(ImgView<T> X, ImgView<T> TS, T* __restrict__ G, T* __restrict__ 
     // steps p0 .. p1: step p needs the planes p-1, p and (z axis on) p+1; plane p+2 lands during step p
     const int p0 = Z_ON ? c.zc0 - 1 : c.zc0, p1 = c.zc1;
     for (int q = p0 - 1; q <= p0 + 1; ++q) sg.issue(tile2_plane<T, Z_ON>(P, q), tile2_slot(q));
+    if (p0 + 2 <= p1 + 1) sg.prefetch(tile2_plane<T, Z_ON>(P, p0 + 2));
     for (int q = p0 - 1; q <= p0 + 1; ++q) sg.land(tile2_slot(q));
     __syncthreads();
     for (int p = p0; p <= p1; ++p) {
         const bool more = p + 2 <= p1 + 1;
         if (more) sg.issue(tile2_plane<T, Z_ON>(P, p + 2), tile2_slot(p + 2));
+        if (p + 3 <= p1 + 1) sg.prefetch(tile2_plane<T, Z_ON>(P, p + 3));      // one plane further ahead, into L2 only
         tile2_step<T, VEC, SCHEME, Z_ON, T_ON, R, TSMODE, NORMS>(st, c, g, P, TS, G, norms, p, tp);
         if (more) sg.land(tile2_slot(p + 2));
         __syncthreads();

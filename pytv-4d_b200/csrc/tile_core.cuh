@@ -312,6 +312,11 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const void* map, unsigned
                  "l"(map), "r"(smem_u32(bar)), "r"(cj), "r"(ci), "r"(ct), "r"(cz)
                  : "memory");
 }
+// The same box into L2 only (no shared memory, no completion): issued one plane further ahead than the load, so that the load finds
+// its lines in L2 whatever the DRAM / far-partition latency of the moment is.
+__device__ __forceinline__ void tma_prefetch_4d(const void* map, int cj, int ci, int ct, int cz) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(cj), "r"(ci), "r"(ct), "r"(cz) : "memory");
+}
 #endif
 
 // Static-mask factors of the work region (clamped), once per CTA.
